@@ -1,0 +1,169 @@
+"""Pin the oracle against the reference itself and write the golden fixtures.
+
+Run in the build container (needs /root/reference; the GPU box never runs this):
+
+    python oracle/make_golden.py
+
+For each model family it (1) executes the reference's own Python (runpy for the flat scripts,
+import for models.py files) under fixed seeds, (2) builds the oracle restatement under the same
+seeds, (3) asserts parameters / outputs / gradients are IDENTICAL (both are stock torch on CPU),
+and (4) stores seeded inputs + the reference's outputs as small fixtures in tests/golden/.
+TEST INFRASTRUCTURE ONLY.
+"""
+import contextlib
+import io
+import os
+import runpy
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("B200GAN_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import ref_models  # noqa: E402
+
+
+class _FakeMNIST(torch.utils.data.Dataset):
+    """Stand-in for torchvision.datasets.MNIST (dcgan.py:121 asks for download=True; no network)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __len__(self):
+        return 1  # DataLoader(shuffle=True) refuses an empty dataset; --n_epochs 0 never iterates it
+
+    def __getitem__(self, i):
+        return torch.zeros(1, 8, 8), 0
+
+
+@contextlib.contextmanager
+def _script_env(argv):
+    import torchvision.datasets as tvd
+    old_argv, old_cwd, old_mnist = sys.argv, os.getcwd(), tvd.MNIST
+    tmp = tempfile.mkdtemp(prefix="b200gan_ref_")
+    work = os.path.join(tmp, "a", "b")
+    os.makedirs(work)
+    tvd.MNIST = _FakeMNIST
+    sys.argv = argv
+    os.chdir(work)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            yield
+    finally:
+        sys.argv = old_argv
+        os.chdir(old_cwd)
+        tvd.MNIST = old_mnist
+
+
+def run_reference_script(rel, args, seed):
+    """Execute an unmodified reference script with n_epochs=0: builds + initialises its models."""
+    path = os.path.join(REF, "implementations", rel)
+    torch.manual_seed(seed)
+    with _script_env([path] + args):
+        return runpy.run_path(path, run_name="__main__")
+
+
+def _assert_same_state(a, b, what):
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys()), f"{what}: state_dict keys differ"
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), f"{what}: parameter {k} differs from the reference"
+
+
+def _grad_digest(model):
+    return {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def golden_dcgan(img_size, batch, seed=0):
+    ref = run_reference_script("dcgan/dcgan.py", ["--n_epochs", "0", "--img_size", str(img_size), "--batch_size",
+                                                  str(batch)], seed)
+    g_ref, d_ref = ref["generator"], ref["discriminator"]
+    g_or, d_or = ref_models.build_dcgan(img_size, seed=seed)
+    _assert_same_state(g_ref, g_or, "dcgan G")
+    _assert_same_state(d_ref, d_or, "dcgan D")
+
+    z = ref_models.synthetic_z(batch, seed=seed)
+    imgs = ref_models.synthetic_images(batch, 1, img_size, img_size, seed=seed)
+    out = {}
+    for tag, (g, d) in {"ref": (g_ref, d_ref), "oracle": (g_or, d_or)}.items():
+        for m in d.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = 0.0  # masks come from a different RNG on the GPU; mask application is tested separately
+        g.train()
+        d.train()
+        g.zero_grad()
+        d.zero_grad()
+        gen = g(z)
+        validity = d(gen)
+        loss = torch.nn.BCELoss()(validity, torch.ones(batch, 1))
+        loss.backward()
+        g_grads = _grad_digest(g)
+        d.zero_grad()
+        real_v = d(imgs)
+        d_loss = (torch.nn.BCELoss()(real_v, torch.ones(batch, 1)) +
+                  torch.nn.BCELoss()(d(gen.detach()), torch.zeros(batch, 1))) / 2
+        d_loss.backward()
+        out[tag] = dict(gen=gen.detach(), validity=validity.detach(), g_loss=loss.detach(), d_loss=d_loss.detach(),
+                        real_v=real_v.detach(), g_grads=g_grads, d_grads=_grad_digest(d),
+                        bn_running={k: v.clone() for k, v in g.state_dict().items() if "running" in k})
+    r, o = out["ref"], out["oracle"]
+    for k in ("gen", "validity", "g_loss", "d_loss", "real_v"):
+        assert torch.equal(r[k], o[k]), f"dcgan {k}: oracle != reference"
+    for k in r["g_grads"]:
+        assert torch.equal(r["g_grads"][k], o["g_grads"][k]), f"dcgan G grad {k}"
+    for k in r["d_grads"]:
+        assert torch.equal(r["d_grads"][k], o["d_grads"][k]), f"dcgan D grad {k}"
+
+    # fixture: inputs + reference outputs; big gradients are stored as (norm, first 64 values)
+    def slim(gr):
+        return {k: dict(norm=v.double().norm().item(), head=v.flatten()[:64].clone(), shape=tuple(v.shape))
+                for k, v in gr.items()}
+
+    fix = dict(img_size=img_size, batch=batch, seed=seed, z=z, imgs=imgs, gen=r["gen"], validity=r["validity"],
+               real_v=r["real_v"], g_loss=r["g_loss"], d_loss=r["d_loss"], g_grads=slim(r["g_grads"]),
+               d_grads=slim(r["d_grads"]), bn_running=r["bn_running"],
+               torch_version=torch.__version__, reference="dcgan/dcgan.py@36d3c77")
+    path = os.path.join(GOLD, f"dcgan_{img_size}_b{batch}.pt")
+    torch.save(fix, path)
+    print(f"dcgan img {img_size} batch {batch}: oracle == reference (bit-exact); wrote {path} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def golden_ops(seed=0):
+    """Operator-level fixtures from stock torch CPU for every conv geometry on the hot path
+    (SURVEY.md section 0.6), small sizes.  Checked against oracle/np_ops.py in the CPU tests."""
+    torch.manual_seed(seed)
+    cases = []
+    specs = [  # (name, cin, cout, k, stride, pad, h, w, transposed)
+        ("k3s1p1", 8, 6, 3, 1, 1, 9, 7, False),
+        ("k3s2p1", 5, 7, 3, 2, 1, 10, 8, False),
+        ("k3s1p0", 4, 4, 3, 1, 0, 8, 8, False),
+        ("k4s2p1", 3, 8, 4, 2, 1, 12, 12, False),
+        ("k4s1p1", 6, 2, 4, 1, 1, 9, 9, False),
+        ("k7s1p0", 3, 5, 7, 1, 0, 14, 14, False),
+        ("t4s2p1", 6, 4, 4, 2, 1, 5, 6, True),
+    ]
+    for name, cin, cout, k, s, p, h, w, tr in specs:
+        x = torch.randn(2, cin, h, w, requires_grad=True)
+        mod = (torch.nn.ConvTranspose2d if tr else torch.nn.Conv2d)(cin, cout, k, s, p)
+        y = mod(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        cases.append(dict(name=name, transposed=tr, stride=s, pad=p, x=x.detach(), w=mod.weight.detach().clone(),
+                          b=mod.bias.detach().clone(), y=y.detach(), gy=gy, gx=x.grad.clone(),
+                          gw=mod.weight.grad.clone(), gb=mod.bias.grad.clone()))
+    path = os.path.join(GOLD, "ops_conv.pt")
+    torch.save(cases, path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    golden_dcgan(32, 8)
+    golden_ops()

@@ -1,0 +1,255 @@
+"""Autograd nodes of the b200gan hot path.  Every forward/backward here is one or more calls into
+libb200gan.so; torch only provides the tensors and the autograd tape.
+
+Reference behaviour mirrored (file:line under implementations/):
+  conv blocks        dcgan/dcgan.py:52-64, 77-88   pix2pix/models.py:20-52   cyclegan/models.py:22-87
+  training-mode BN   dcgan/dcgan.py:53,56,60,80 (eps = 0.8)    InstanceNorm  pix2pix/models.py:25,40
+"""
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ALGO_AUTO, ALGO_SIMT, ALGO_TC, PACK_SIMT_DGRAD,
+                   PACK_SIMT_FPROP, PACK_TC_DGRAD, PACK_TC_DGRAD_UP2, PACK_TC_FPROP, PACK_TC_FPROP_UP2, PAD_ZERO)
+
+
+@dataclass(frozen=True)
+class ConvSpec:
+    stride: int = 1
+    pads: Tuple[int, int, int, int] = (0, 0, 0, 0)  # top, left, bottom, right of the virtual input
+    pad_mode: int = PAD_ZERO
+    up: int = 1
+    transposed: bool = False
+    act: int = ACT_NONE
+    slope: float = 0.0
+    stats: Optional[bool] = None  # None: no fused statistics; False: per channel (BN); True: per sample (IN)
+    rtf_out: bool = False         # round the output to TF32 (it feeds a tcgen05 conv)
+    rtf_dz: bool = False          # round the epilogue-backward output (feeds tcgen05 dgrad/wgrad)
+
+
+@dataclass(frozen=True)
+class NormSpec:
+    per_sample: bool = False
+    eps: float = 1e-5
+    momentum: float = 0.1
+    act: int = ACT_NONE
+    slope: float = 0.0
+    rtf_out: bool = False
+    rtf_dx: bool = False
+
+
+class PackCache:
+    """Derived packed copies of one weight Parameter, invalidated by the tensor version counter."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, g, w, kind):
+        key = (kind, g.C, g.K, g.R, g.S, g.transposed)
+        ver = (w._version, w.data_ptr())
+        hit = self._d.get(key)
+        if ops.Config.weight_cache and hit is not None and hit[0] == ver:
+            return hit[1]
+        packed = ops.pack_weights(g, w, kind)
+        self._d[key] = (ver, packed)
+        return packed
+
+
+def _as_cl(t):
+    return t if ops.is_cl(t) else ops.to_cl(t)
+
+
+class ConvFn(torch.autograd.Function):
+    """[Upsample x2] [pad] Conv2d/ConvTranspose2d [+bias] [act] [* Dropout2d scale] (+ BN/IN partial sums)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, chan_scale, spec: ConvSpec, cache: PackCache):
+        ops._require_cuda(x, "conv input")
+        ops._require_cuda(weight, "conv weight")
+        x = _as_cl(x)
+        g, _ = ops.make_geom(tuple(x.shape), tuple(weight.shape), spec.stride, spec.pads, spec.pad_mode, spec.up,
+                             spec.transposed)
+        w = weight.detach()
+        if ops.tc_supported(g, 0):
+            algo = ALGO_TC
+            packed = cache.get(g, w, PACK_TC_FPROP_UP2 if spec.up == 2 else PACK_TC_FPROP)
+        else:
+            algo = ALGO_SIMT
+            packed = cache.get(g, w, PACK_SIMT_FPROP)
+        stats = None
+        if spec.stats is not None:
+            stats = torch.zeros(2 * (g.N * g.K if spec.stats else g.K), device=x.device, dtype=torch.float64)
+        fuse_stats = stats is not None and not (algo == ALGO_TC and spec.stats)
+        y = ops.conv_fprop(g, x, packed, algo, bias=None if bias is None else bias.detach(), act=spec.act,
+                           slope=spec.slope, chan_scale=chan_scale, stats=stats if fuse_stats else None,
+                           stats_per_sample=bool(spec.stats), round_tf32=spec.rtf_out)
+        if stats is not None and not fuse_stats:
+            stats = None  # caller computes them with a separate pass
+        ctx.spec, ctx.cache, ctx.g = spec, cache, g
+        ctx.has_bias = bias is not None
+        need_y = spec.act != ACT_NONE
+        ctx.save_for_backward(x, weight, y if need_y else None, chan_scale)
+        if spec.stats is not None:
+            if stats is None:
+                stats = torch.empty(0, device=x.device, dtype=torch.float64)
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        x, weight, y, chan_scale = ctx.saved_tensors
+        spec, g = ctx.spec, ctx.g
+        dy = _as_cl(dy)
+        if spec.act != ACT_NONE or chan_scale is not None:
+            dz = ops.epilogue_bwd(dy, y, chan_scale, spec.act, spec.slope, spec.rtf_dz)
+        else:
+            dz = dy
+        dx = dw = db = None
+        w = weight.detach()
+        if ctx.needs_input_grad[0]:
+            if ops.tc_supported(g, 1):
+                packed = ctx.cache.get(g, w, PACK_TC_DGRAD_UP2 if spec.up == 2 else PACK_TC_DGRAD)
+                dx = ops.conv_dgrad(g, dz, packed, ALGO_TC)
+            else:
+                packed = ctx.cache.get(g, w, PACK_SIMT_DGRAD)
+                dx = ops.conv_dgrad(g, dz, packed, ALGO_SIMT)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            algo = ALGO_SIMT if ops.Config.algo == "simt" else ALGO_AUTO
+            dw, db = ops.conv_wgrad(g, x, dz, tuple(weight.shape), ctx.has_bias and ctx.needs_input_grad[2], algo)
+            if not ctx.needs_input_grad[1]:
+                dw = None
+        return dx, dw, db, None, None, None
+
+
+class NormFn(torch.autograd.Function):
+    """Training-mode BatchNorm2d / InstanceNorm2d with an optional fused activation."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, stats, running_mean, running_var, nbt, spec: NormSpec):
+        ops._require_cuda(x, "norm input")
+        x = _as_cl(x)
+        if stats is not None and stats.numel() == 0:
+            stats = None
+        y, mean_rstd = ops.norm_forward(
+            x, None if gamma is None else gamma.detach(), None if beta is None else beta.detach(), running_mean,
+            running_var, nbt, spec.per_sample, spec.eps, spec.momentum, spec.act, spec.slope, stats, spec.rtf_out)
+        ctx.spec = spec
+        ctx.save_for_backward(x, y if spec.act != ACT_NONE else None, mean_rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean_rstd, gamma = ctx.saved_tensors
+        spec = ctx.spec
+        dy = _as_cl(dy)
+        need_params = gamma is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        dx, dgb = ops.norm_backward(dy, x, y, mean_rstd, None if gamma is None else gamma.detach(), spec.per_sample,
+                                    spec.eps, spec.act, spec.slope, need_params, spec.rtf_dx)
+        dgamma = dbeta = None
+        if need_params:
+            n, c = x.shape[0], x.shape[1]
+            groups = dgb.numel() // 2
+            dgamma, dbeta = dgb[:groups], dgb[groups:]
+            if spec.per_sample:  # affine InstanceNorm2d: parameters are shared across samples
+                dgamma, dbeta = dgamma.view(n, c).sum(0), dbeta.view(n, c).sum(0)
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+class AffineActFn(torch.autograd.Function):
+    """y = act(x * scale[c] + shift[c]) with constant scale/shift: eval-mode BatchNorm2d."""
+
+    @staticmethod
+    def forward(ctx, x, scale_shift, act, slope):
+        x = _as_cl(x)
+        y = ops.norm_apply_affine(x, scale_shift, False, act, slope)
+        ctx.act, ctx.slope = act, slope
+        ctx.save_for_backward(y, scale_shift)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, scale_shift = ctx.saved_tensors
+        dy = _as_cl(dy)
+        dz = ops.epilogue_bwd(dy, y, None, ctx.act, ctx.slope) if ctx.act != ACT_NONE else dy
+        c = y.shape[1]
+        zero = torch.zeros_like(scale_shift)
+        zero[:c] = scale_shift[:c]
+        # dx = dz * scale: an affine apply with shift = 0
+        return ops.norm_apply_affine(dz, zero, False), None, None, None
+
+
+class ToChannelsLastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.to_cl(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.to_nchw(dy)
+
+
+class ToContiguousFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.to_nchw(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _as_cl(dy)
+
+
+class UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2x(_as_cl(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.upsample2x_bwd(_as_cl(dy))
+
+
+class PadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pads, mode):
+        ctx.pads, ctx.mode = pads, mode
+        return ops.pad2d(_as_cl(x), pads, mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.pad2d_bwd(_as_cl(dy), ctx.pads, ctx.mode), None, None
+
+
+class ActFn(torch.autograd.Function):
+    """y = mask * act(x).  mask: None, per-(n,c) [N,C] (Dropout2d) or element-wise (Dropout)."""
+
+    @staticmethod
+    def forward(ctx, x, act, slope, mask, mask_per_channel):
+        x = _as_cl(x)
+        y = ops.act_forward(x, act, slope, mask, mask_per_channel)
+        ctx.act, ctx.slope, ctx.mpc = act, slope, mask_per_channel
+        ctx.save_for_backward(y if act != ACT_NONE else None, mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, mask = ctx.saved_tensors
+        dy = _as_cl(dy)
+        if mask is not None and not ctx.mpc:
+            if ctx.act in (ACT_TANH, ACT_SIGMOID):
+                raise NotImplementedError("b200gan: element-wise mask fused with tanh/sigmoid")
+            dy = ops.act_forward(dy, ACT_NONE, 0.0, mask, False)
+            mask = None
+        if ctx.act == ACT_NONE and mask is None:
+            return dy, None, None, None, None
+        return ops.epilogue_bwd(dy, y, mask, ctx.act, ctx.slope), None, None, None, None
+
+
+def conv_block(x, weight, bias, chan_scale, spec, cache):
+    return ConvFn.apply(x, weight, bias, chan_scale, spec, cache)
+
+
+def norm_block(x, gamma, beta, stats, running_mean, running_var, nbt, spec):
+    return NormFn.apply(x, gamma, beta, stats, running_mean, running_var, nbt, spec)

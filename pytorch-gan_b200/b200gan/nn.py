@@ -1,0 +1,369 @@
+"""Drop-in replacements for the torch.nn leaf modules the reference's Generator/Discriminator
+classes instantiate.  Same constructor and forward signatures, same class
+*names* (the reference's weights_init_normal dispatches on `__class__.__name__`, dcgan.py:36-42),
+same Parameters / buffers / state_dict keys -- the arithmetic runs in libb200gan.so.
+
+`Sequential` keeps the module tree the scripts build (dcgan.py:52-64, 83-88) and fuses at call
+time: [Upsample][Pad] Conv [act][Dropout2d] (+ statistics for a following norm) and Norm [act]
+become single fused nodes; anything unknown is executed leaf by leaf.
+
+There is no CPU / cuDNN fallback for the conv and norm modules: CPU tensors raise.
+"""
+import torch
+import torch.nn as tnn
+
+from . import functional as F
+from . import ops
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, PAD_REFLECT, PAD_ZERO)
+from .functional import ConvSpec, NormSpec, PackCache
+
+_T = {  # the stock classes, captured before any patching
+    n: getattr(tnn, n) for n in (
+        "Conv2d", "ConvTranspose2d", "BatchNorm2d", "InstanceNorm2d", "LeakyReLU", "ReLU", "Tanh", "Sigmoid",
+        "Upsample", "ZeroPad2d", "ReflectionPad2d", "Dropout", "Dropout2d", "Sequential")
+}
+
+
+def _pair_same(v, what):
+    if isinstance(v, (tuple, list)):
+        if len(v) != 2 or v[0] != v[1]:
+            raise NotImplementedError(f"b200gan: {what}={v} (h != w) is not supported")
+        return int(v[0])
+    return int(v)
+
+
+def _act_of(m):
+    if isinstance(m, _T["LeakyReLU"]):
+        return ACT_LRELU, float(m.negative_slope)
+    if isinstance(m, _T["ReLU"]):
+        return ACT_RELU, 0.0
+    if isinstance(m, _T["Tanh"]):
+        return ACT_TANH, 0.0
+    if isinstance(m, _T["Sigmoid"]):
+        return ACT_SIGMOID, 0.0
+    return None
+
+
+def _is_up2(m):
+    if not isinstance(m, _T["Upsample"]):
+        return False
+    sf = m.scale_factor
+    if isinstance(sf, (tuple, list)):
+        sf = sf[0] if len(set(sf)) == 1 else None
+    return m.size is None and sf is not None and float(sf) == 2.0 and m.mode == "nearest"
+
+
+def _pads_of(m):
+    """torch padding order (left, right, top, bottom) -> (top, left, bottom, right)."""
+    p = m.padding
+    if isinstance(p, int):
+        p = (p, p, p, p)
+    l, r, t, b = p
+    return (int(t), int(l), int(b), int(r))
+
+
+def _conv_ok(m):
+    if isinstance(m.padding, str) or m.padding_mode != "zeros":
+        return False
+    if tuple(m.dilation) != (1, 1) or m.groups != 1:
+        return False
+    if len(set(m.stride)) != 1 or len(set(m.padding)) != 1:
+        return False
+    if isinstance(m, _T["ConvTranspose2d"]) and tuple(m.output_padding) != (0, 0):
+        return False
+    return True
+
+
+def _tc_like(conv, up):
+    """Static mirror of tc_supported() used to decide where TF32 rounding of operands pays."""
+    if ops.Config.algo == "simt" or isinstance(conv, _T["ConvTranspose2d"]):
+        return False
+    return conv.stride[0] == 1 and conv.in_channels % 32 == 0 and conv.out_channels % 64 == 0
+
+
+def _dropout2d_scale(x_shape, p, device):
+    """Exactly the draw F.dropout2d makes (feature_dropout: noise [N,C,1,1] ~ Bernoulli(1-p) / (1-p)),
+    so masks are bit-identical to the reference's under the same seed (dcgan.py:77)."""
+    n, c = x_shape[0], x_shape[1]
+    noise = torch.empty((n, c, 1, 1), device=device, dtype=torch.float32)
+    if p >= 1.0:
+        return noise.zero_().view(n, c)
+    return noise.bernoulli_(1.0 - p).div_(1.0 - p).view(n, c)
+
+
+def _run_conv(conv, x, up=1, extra_pads=(0, 0, 0, 0), pad_mode=PAD_ZERO, act=ACT_NONE, slope=0.0, chan_scale=None,
+              stats=None, rtf_out=False, rtf_dz=False):
+    if not _conv_ok(conv):
+        raise NotImplementedError(f"b200gan: unsupported convolution configuration: {conv}")
+    transposed = isinstance(conv, _T["ConvTranspose2d"])
+    pad = int(conv.padding[0])
+    if pad_mode == PAD_REFLECT and pad != 0:
+        raise NotImplementedError("b200gan: reflection padding in front of a zero-padded conv")
+    pads = tuple(e + pad for e in extra_pads)
+    spec = ConvSpec(stride=int(conv.stride[0]), pads=pads, pad_mode=pad_mode, up=up, transposed=transposed, act=act,
+                    slope=slope, stats=stats, rtf_out=rtf_out, rtf_dz=rtf_dz)
+    cache = conv.__dict__.get("_b200_cache")
+    if cache is None:
+        cache = PackCache()
+        conv.__dict__["_b200_cache"] = cache
+    return F.conv_block(x, conv.weight, conv.bias, chan_scale, spec, cache)
+
+
+def _run_norm(norm, x, act=ACT_NONE, slope=0.0, stats=None, rtf_out=False, rtf_dx=False):
+    per_sample = isinstance(norm, _T["InstanceNorm2d"])
+    if per_sample and norm.track_running_stats:
+        raise NotImplementedError("b200gan: InstanceNorm2d(track_running_stats=True)")
+    if x.dim() != 4:
+        raise ValueError(f"expected 4D input (got {x.dim()}D input)")
+    if per_sample and x.shape[2] * x.shape[3] == 1 and norm.training:
+        raise ValueError(f"Expected more than 1 spatial element when training, got input size {tuple(x.shape)}")
+    use_batch_stats = per_sample or norm.training or norm.running_mean is None
+    if use_batch_stats:
+        rm = rv = nbt = None
+        momentum = 0.0
+        if not per_sample and norm.training and norm.track_running_stats:
+            if norm.momentum is None:
+                raise NotImplementedError("b200gan: BatchNorm2d(momentum=None)")
+            rm, rv, nbt, momentum = norm.running_mean, norm.running_var, norm.num_batches_tracked, float(norm.momentum)
+        spec = NormSpec(per_sample=per_sample, eps=float(norm.eps), momentum=momentum, act=act, slope=slope,
+                        rtf_out=rtf_out, rtf_dx=rtf_dx)
+        return F.norm_block(x, norm.weight, norm.bias, stats, rm, rv, nbt, spec)
+    # eval-mode BatchNorm2d: constant per-channel affine
+    rstd = torch.rsqrt(norm.running_var + norm.eps)
+    scale = rstd if norm.weight is None else norm.weight * rstd
+    shift = -norm.running_mean * scale if norm.bias is None else norm.bias - norm.running_mean * scale
+    return F.AffineActFn.apply(x, torch.cat([scale, shift]).detach(), act, slope)
+
+
+def _gpu4d(x):
+    return x.dim() == 4 and x.is_cuda
+
+
+# ---- leaf modules ----------------------------------------------------------------------------------
+class Conv2d(_T["Conv2d"]):
+    def forward(self, x):
+        return _run_conv(self, x)
+
+
+class ConvTranspose2d(_T["ConvTranspose2d"]):
+    def forward(self, x, output_size=None):
+        if output_size is not None:
+            raise NotImplementedError("b200gan: ConvTranspose2d(output_size=...)")
+        return _run_conv(self, x)
+
+
+class BatchNorm2d(_T["BatchNorm2d"]):
+    def forward(self, x):
+        return _run_norm(self, x)
+
+
+class InstanceNorm2d(_T["InstanceNorm2d"]):
+    def forward(self, x):
+        return _run_norm(self, x)
+
+
+class _Act:
+    def forward(self, x):
+        if not _gpu4d(x):
+            return super().forward(x)  # MLP / CPU use of the same class (gan.py, wgan_gp.py): stock op
+        act, slope = _act_of(self)
+        return F.ActFn.apply(x, act, slope, None, False)
+
+
+class LeakyReLU(_Act, _T["LeakyReLU"]):
+    pass
+
+
+class ReLU(_Act, _T["ReLU"]):
+    pass
+
+
+class Tanh(_Act, _T["Tanh"]):
+    pass
+
+
+class Sigmoid(_Act, _T["Sigmoid"]):
+    pass
+
+
+class Upsample(_T["Upsample"]):
+    def forward(self, x):
+        if _gpu4d(x) and _is_up2(self):
+            return F.UpsampleFn.apply(x)
+        if _gpu4d(x):
+            raise NotImplementedError(f"b200gan: {self} (only nearest x2 is on the hot path)")
+        return super().forward(x)
+
+
+class ZeroPad2d(_T["ZeroPad2d"]):
+    def forward(self, x):
+        if not _gpu4d(x):
+            return super().forward(x)
+        return F.PadFn.apply(x, _pads_of(self), PAD_ZERO)
+
+
+class ReflectionPad2d(_T["ReflectionPad2d"]):
+    def forward(self, x):
+        if not _gpu4d(x):
+            return super().forward(x)
+        return F.PadFn.apply(x, _pads_of(self), PAD_REFLECT)
+
+
+class Dropout2d(_T["Dropout2d"]):
+    def forward(self, x):
+        if not _gpu4d(x):
+            return super().forward(x)
+        if not self.training or self.p == 0.0:
+            return x
+        return F.ActFn.apply(x, ACT_NONE, 0.0, _dropout2d_scale(x.shape, self.p, x.device), True)
+
+
+class Dropout(_T["Dropout"]):
+    def forward(self, x):
+        if not _gpu4d(x):
+            return super().forward(x)
+        if not self.training or self.p == 0.0:
+            return x
+        xc = x if ops.is_cl(x) else ops.to_cl(x)
+        mask = torch.empty_like(xc, memory_format=torch.channels_last)
+        if self.p >= 1.0:
+            mask.zero_()
+        else:
+            mask.bernoulli_(1.0 - self.p).div_(1.0 - self.p)
+        return F.ActFn.apply(xc, ACT_NONE, 0.0, mask, False)
+
+
+# ---- fusion planner ------------------------------------------------------------------------------------
+class _ConvStep:
+    def __init__(self, conv, up, extra_pads, pad_mode, act, slope, dropout2d, stats):
+        self.conv, self.up, self.extra_pads, self.pad_mode = conv, up, extra_pads, pad_mode
+        self.act, self.slope, self.dropout2d, self.stats = act, slope, dropout2d, stats
+        self.rtf_out = False
+        self.rtf_dz = False
+
+    def tc_like(self):
+        return self.pad_mode == PAD_ZERO and _tc_like(self.conv, self.up)
+
+
+class _NormStep:
+    def __init__(self, norm, act, slope, takes_stats):
+        self.norm, self.act, self.slope, self.takes_stats = norm, act, slope, takes_stats
+        self.rtf_out = False
+        self.rtf_dx = False
+
+
+class _LeafStep:
+    def __init__(self, mod):
+        self.mod = mod
+
+
+def _is_norm(m):
+    return isinstance(m, (_T["BatchNorm2d"], _T["InstanceNorm2d"]))
+
+
+def _build_plan(mods):
+    steps, i, n = [], 0, len(mods)
+    while i < n:
+        j, up, extra, mode = i, 1, (0, 0, 0, 0), PAD_ZERO
+        if _is_up2(mods[j]):
+            up, j = 2, j + 1
+        if j < n and isinstance(mods[j], (_T["ZeroPad2d"], _T["ReflectionPad2d"])):
+            extra = _pads_of(mods[j])
+            mode = PAD_REFLECT if isinstance(mods[j], _T["ReflectionPad2d"]) else PAD_ZERO
+            j += 1
+        conv = mods[j] if j < n else None
+        is_conv = isinstance(conv, (_T["Conv2d"], _T["ConvTranspose2d"])) and _conv_ok(conv)
+        if is_conv and isinstance(conv, _T["ConvTranspose2d"]) and (up != 1 or j != i):
+            is_conv = False
+        if is_conv and mode == PAD_REFLECT and int(conv.padding[0]) != 0:
+            is_conv = False
+        if is_conv:
+            j += 1
+            act, slope, d2 = ACT_NONE, 0.0, None
+            if j < n and _act_of(mods[j]) is not None:
+                act, slope = _act_of(mods[j])
+                j += 1
+            if j < n and isinstance(mods[j], _T["Dropout2d"]):
+                d2 = mods[j]
+                j += 1
+            stats = None
+            if j < n and _is_norm(mods[j]):
+                stats = isinstance(mods[j], _T["InstanceNorm2d"])
+            steps.append(_ConvStep(conv, up, extra, mode, act, slope, d2, stats))
+            i = j
+            continue
+        m = mods[i]
+        if _is_norm(m):
+            j = i + 1
+            act, slope = ACT_NONE, 0.0
+            if j < n and _act_of(mods[j]) is not None:
+                act, slope = _act_of(mods[j])
+                j += 1
+            prev = steps[-1] if steps else None
+            takes = isinstance(prev, _ConvStep) and prev.stats is not None
+            steps.append(_NormStep(m, act, slope, takes))
+            i = j
+            continue
+        steps.append(_LeafStep(m))
+        i += 1
+    # TF32 operand rounding: producers that feed a tensor-core conv store RN-rounded values
+    for k, s in enumerate(steps):
+        if isinstance(s, _ConvStep) and s.tc_like():
+            if k > 0 and isinstance(steps[k - 1], (_ConvStep, _NormStep)):
+                steps[k - 1].rtf_out = True
+            s.rtf_dz = True
+            if k + 1 < len(steps) and isinstance(steps[k + 1], _NormStep):
+                steps[k + 1].rtf_dx = True
+    return steps
+
+
+class Sequential(_T["Sequential"]):
+    def _plan(self):
+        mods = list(self._modules.values())
+        key = tuple(id(m) for m in mods) + (ops.Config.algo,)
+        cached = self.__dict__.get("_b200_plan")
+        if cached is None or cached[0] != key:
+            cached = (key, _build_plan(mods))
+            self.__dict__["_b200_plan"] = cached
+        return cached[1]
+
+    def forward(self, x):
+        if not (torch.is_tensor(x) and x.dim() == 4 and x.is_cuda and x.dtype == torch.float32):
+            return super().forward(x)
+        steps = self._plan()
+        if all(isinstance(s, _LeafStep) for s in steps):
+            return super().forward(x)
+        want_contiguous = x.is_contiguous()  # output memory format follows the input's
+        stats = None
+        for s in steps:
+            if isinstance(s, _ConvStep):
+                cs = None
+                if s.dropout2d is not None and s.dropout2d.training and s.dropout2d.p > 0.0:
+                    n = x.shape[0]
+                    cs = _dropout2d_scale((n, s.conv.out_channels), s.dropout2d.p, x.device)
+                out = _run_conv(s.conv, x, s.up, s.extra_pads, s.pad_mode, s.act, s.slope, cs, s.stats, s.rtf_out,
+                                s.rtf_dz)
+                if s.stats is not None:
+                    x, stats = out
+                else:
+                    x, stats = out, None
+            elif isinstance(s, _NormStep):
+                x = _run_norm(s.norm, x, s.act, s.slope, stats if s.takes_stats else None, s.rtf_out, s.rtf_dx)
+                stats = None
+            else:
+                x = s.mod(x)
+                stats = None
+        if want_contiguous and torch.is_tensor(x) and x.dim() == 4 and not x.is_contiguous():
+            x = F.ToContiguousFn.apply(x)
+        return x
+
+
+REPLACEMENTS = {
+    "Conv2d": Conv2d, "ConvTranspose2d": ConvTranspose2d, "BatchNorm2d": BatchNorm2d,
+    "InstanceNorm2d": InstanceNorm2d, "LeakyReLU": LeakyReLU, "ReLU": ReLU, "Tanh": Tanh, "Sigmoid": Sigmoid,
+    "Upsample": Upsample, "ZeroPad2d": ZeroPad2d, "ReflectionPad2d": ReflectionPad2d, "Dropout": Dropout,
+    "Dropout2d": Dropout2d, "Sequential": Sequential,
+}
+for _n, _c in REPLACEMENTS.items():
+    _c.__name__ = _n
+    _c.__qualname__ = _n

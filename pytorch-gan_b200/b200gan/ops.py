@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI (include/b200gan.h).
+
+Activations are torch tensors of logical shape [N, C, H, W] whose memory is NHWC
+(`torch.channels_last`).  Nothing here differentiates; autograd lives in functional.py.
+PyTorch is used for device memory (caching allocator), streams and tensor plumbing only.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ALGO_SIMT, ALGO_TC, PAD_REFLECT, PAD_ZERO, ConvGeom, Epilogue, NormDesc)
+
+CL = torch.channels_last
+
+
+class Config:
+    """Global switches. `algo`: 'auto' (tcgen05 where the geometry qualifies) or 'simt'."""
+    algo = "auto"
+    weight_cache = True
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"b200gan: {name} is on {t.device}; the b200gan product path runs on CUDA only "
+                           "(no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"b200gan: {name} has dtype {t.dtype}; fp32 expected")
+
+
+def is_cl(x):
+    return x.dim() == 4 and x.is_contiguous(memory_format=CL)
+
+
+def empty_cl(n, c, h, w, device):
+    return torch.empty((n, c, h, w), device=device, dtype=torch.float32, memory_format=CL)
+
+
+def to_cl(x):
+    """NCHW-contiguous -> NHWC memory (our transpose kernel); no-op if already channels_last."""
+    _require_cuda(x, "input")
+    if is_cl(x):
+        return x
+    if not x.is_contiguous():
+        x = x.contiguous()
+    n, c, h, w = x.shape
+    y = empty_cl(n, c, h, w, x.device)
+    _lib.check(_lib.load().b200gan_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), n, c, h * w, _stream()), "nchw_to_nhwc")
+    return y
+
+
+def to_nchw(x):
+    """NHWC memory -> NCHW-contiguous tensor (needed where scripts call .view, dcgan.py:96)."""
+    _require_cuda(x, "input")
+    if x.is_contiguous():
+        return x
+    if not is_cl(x):
+        return x.contiguous()
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().b200gan_nhwc_to_nchw(x.data_ptr(), y.data_ptr(), n, c, h * w, _stream()), "nhwc_to_nchw")
+    return y
+
+
+# ---- convolution -------------------------------------------------------------------------------
+def make_geom(x_shape, weight_shape, stride, pads, pad_mode=PAD_ZERO, up=1, transposed=False):
+    """pads = (top, left, bottom, right) of the virtual input. Returns (ConvGeom, out_shape)."""
+    n, c, h, w = x_shape
+    g = ConvGeom()
+    g.N, g.H, g.W, g.C = n, h, w, c
+    if transposed:
+        cin, cout, r, s = weight_shape
+    else:
+        cout, cin, r, s = weight_shape
+    if cin != c:
+        raise RuntimeError(f"b200gan conv: input has {c} channels, weight expects {cin}")
+    g.K, g.R, g.S, g.stride = cout, r, s, stride
+    g.pad_t, g.pad_l, g.pad_b, g.pad_r = pads
+    g.pad_mode, g.up, g.transposed = pad_mode, up, int(transposed)
+    if transposed:
+        g.P = (h - 1) * stride - 2 * pads[0] + r
+        g.Q = (w - 1) * stride - 2 * pads[1] + s
+    else:
+        g.P = (h * up + pads[0] + pads[2] - r) // stride + 1
+        g.Q = (w * up + pads[1] + pads[3] - s) // stride + 1
+    return g, (n, cout, g.P, g.Q)
+
+
+def tc_supported(g, pas):
+    if Config.algo == "simt":
+        return False
+    return bool(_lib.load().b200gan_conv2d_supported(ctypes.byref(g), pas, ALGO_TC))
+
+
+def pack_weights(g, w, kind):
+    lib = _lib.load()
+    n = lib.b200gan_packed_weight_floats(ctypes.byref(g), kind)
+    out = torch.empty(n, device=w.device, dtype=torch.float32)
+    _lib.check(lib.b200gan_pack_weights(ctypes.byref(g), kind, w.data_ptr(), out.data_ptr(), _stream()), "pack_weights")
+    return out
+
+
+def conv_fprop(g, x, packed, algo, bias=None, act=ACT_NONE, slope=0.0, chan_scale=None, stats=None,
+               stats_per_sample=False, round_tf32=False):
+    y = empty_cl(g.N, g.K, g.P, g.Q, x.device)
+    ep = Epilogue()
+    ep.bias, ep.act, ep.slope = _ptr(bias), act, slope
+    ep.chan_scale, ep.stats = _ptr(chan_scale), _ptr(stats)
+    ep.stats_per_sample, ep.round_tf32 = int(stats_per_sample), int(round_tf32)
+    _lib.check(_lib.load().b200gan_conv2d_fprop(ctypes.byref(g), ctypes.byref(ep), x.data_ptr(), packed.data_ptr(),
+                                                y.data_ptr(), algo, _stream()), "conv2d_fprop")
+    return y
+
+
+def conv_dgrad(g, dy, packed, algo):
+    lib = _lib.load()
+    dx = empty_cl(g.N, g.C, g.H, g.W, dy.device)
+    nws = lib.b200gan_conv2d_dgrad_workspace_floats(ctypes.byref(g), algo)
+    ws = torch.empty(nws, device=dy.device, dtype=torch.float32) if nws else None
+    _lib.check(lib.b200gan_conv2d_dgrad(ctypes.byref(g), dy.data_ptr(), packed.data_ptr(), dx.data_ptr(), _ptr(ws),
+                                        algo, _stream()), "conv2d_dgrad")
+    return dx
+
+
+def conv_wgrad(g, x, dy, weight_shape, need_bias, algo):
+    lib = _lib.load()
+    dw = torch.empty(weight_shape, device=x.device, dtype=torch.float32)
+    db = torch.empty(g.K, device=x.device, dtype=torch.float32) if need_bias else None
+    nws = lib.b200gan_conv2d_wgrad_workspace_floats(ctypes.byref(g), algo)
+    ws = torch.empty(nws, device=x.device, dtype=torch.float32) if nws else None
+    _lib.check(lib.b200gan_conv2d_wgrad(ctypes.byref(g), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db),
+                                        _ptr(ws), algo, _stream()), "conv2d_wgrad")
+    return dw, db
+
+
+def epilogue_bwd(dy, y, chan_scale, act, slope, round_tf32=False):
+    n, k, p, q = dy.shape
+    dz = torch.empty_like(dy, memory_format=CL)
+    _lib.check(_lib.load().b200gan_epilogue_bwd(dy.data_ptr(), _ptr(y), _ptr(chan_scale), act, slope, dy.numel(), k,
+                                                p * q, int(round_tf32), dz.data_ptr(), _stream()), "epilogue_bwd")
+    return dz
+
+
+# ---- normalisation -----------------------------------------------------------------------------
+def _norm_desc(x, per_sample, eps, momentum, act, slope, round_tf32):
+    n, c, h, w = x.shape
+    d = NormDesc()
+    d.N, d.HW, d.C, d.per_sample = n, h * w, c, int(per_sample)
+    d.eps, d.momentum, d.act, d.slope, d.round_tf32 = eps, momentum, act, slope, int(round_tf32)
+    return d
+
+
+def new_stats(x, per_sample):
+    n, c = x.shape[0], x.shape[1]
+    return torch.zeros(2 * (n * c if per_sample else c), device=x.device, dtype=torch.float64)
+
+
+def norm_forward(x, gamma, beta, running_mean, running_var, nbt, per_sample, eps, momentum, act=ACT_NONE, slope=0.0,
+                 stats=None, round_tf32=False):
+    """Training-mode BatchNorm2d / InstanceNorm2d.  Returns (y, mean_rstd)."""
+    lib = _lib.load()
+    d = _norm_desc(x, per_sample, eps, momentum, act, slope, round_tf32)
+    st = _stream()
+    if stats is None:
+        stats = new_stats(x, per_sample)
+        _lib.check(lib.b200gan_norm_stats(ctypes.byref(d), x.data_ptr(), stats.data_ptr(), st), "norm_stats")
+    groups = stats.numel() // 2
+    mean_rstd = torch.empty(2 * groups, device=x.device, dtype=torch.float32)
+    scale_shift = torch.empty(2 * groups, device=x.device, dtype=torch.float32)
+    _lib.check(lib.b200gan_norm_finalize(ctypes.byref(d), stats.data_ptr(), _ptr(gamma), _ptr(beta),
+                                         mean_rstd.data_ptr(), scale_shift.data_ptr(), _ptr(running_mean),
+                                         _ptr(running_var), _ptr(nbt), st), "norm_finalize")
+    y = torch.empty_like(x, memory_format=CL)
+    _lib.check(lib.b200gan_norm_apply(ctypes.byref(d), x.data_ptr(), scale_shift.data_ptr(), y.data_ptr(), st),
+               "norm_apply")
+    return y, mean_rstd
+
+
+def norm_apply_affine(x, scale_shift, per_sample, act=ACT_NONE, slope=0.0):
+    """y = act(x * scale + shift) with precomputed per-group scale/shift (eval-mode BatchNorm)."""
+    d = _norm_desc(x, per_sample, 0.0, 0.0, act, slope, False)
+    y = torch.empty_like(x, memory_format=CL)
+    _lib.check(_lib.load().b200gan_norm_apply(ctypes.byref(d), x.data_ptr(), scale_shift.data_ptr(), y.data_ptr(),
+                                              _stream()), "norm_apply")
+    return y
+
+
+def norm_backward(dy, x, y, mean_rstd, gamma, per_sample, eps, act=ACT_NONE, slope=0.0, need_params=False,
+                  round_tf32=False):
+    lib = _lib.load()
+    d = _norm_desc(x, per_sample, eps, 0.0, act, slope, round_tf32)
+    groups = mean_rstd.numel() // 2
+    sums = torch.zeros(2 * groups, device=x.device, dtype=torch.float64)
+    dx = torch.empty_like(x, memory_format=CL)
+    dgb = torch.empty(2 * groups, device=x.device, dtype=torch.float32) if need_params else None
+    _lib.check(lib.b200gan_norm_bwd(ctypes.byref(d), dy.data_ptr(), x.data_ptr(), _ptr(y), mean_rstd.data_ptr(),
+                                    _ptr(gamma), sums.data_ptr(), dx.data_ptr(), _ptr(dgb), _stream()), "norm_bwd")
+    return dx, dgb
+
+
+# ---- shape ops ------------------------------------------------------------------------------------
+def upsample2x(x):
+    n, c, h, w = x.shape
+    y = empty_cl(n, c, 2 * h, 2 * w, x.device)
+    _lib.check(_lib.load().b200gan_upsample2x_fwd(x.data_ptr(), y.data_ptr(), n, h, w, c, _stream()), "upsample2x_fwd")
+    return y
+
+
+def upsample2x_bwd(dy):
+    n, c, h2, w2 = dy.shape
+    dx = empty_cl(n, c, h2 // 2, w2 // 2, dy.device)
+    _lib.check(_lib.load().b200gan_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), n, h2 // 2, w2 // 2, c, _stream()),
+               "upsample2x_bwd")
+    return dx
+
+
+def pad2d(x, pads, mode):
+    n, c, h, w = x.shape
+    t, l, b, r = pads
+    y = empty_cl(n, c, h + t + b, w + l + r, x.device)
+    _lib.check(_lib.load().b200gan_pad2d_fwd(x.data_ptr(), y.data_ptr(), n, h, w, c, t, l, b, r, mode, _stream()),
+               "pad2d_fwd")
+    return y
+
+
+def pad2d_bwd(dy, pads, mode):
+    n, c, ho, wo = dy.shape
+    t, l, b, r = pads
+    h, w = ho - t - b, wo - l - r
+    dx = empty_cl(n, c, h, w, dy.device)
+    _lib.check(_lib.load().b200gan_pad2d_bwd(dy.data_ptr(), dx.data_ptr(), n, h, w, c, t, l, b, r, mode, _stream()),
+               "pad2d_bwd")
+    return dx
+
+
+def act_forward(x, act, slope, mask=None, mask_per_channel=False):
+    n, c, h, w = x.shape
+    y = torch.empty_like(x, memory_format=CL)
+    _lib.check(_lib.load().b200gan_act_fwd(x.data_ptr(), _ptr(mask), int(mask_per_channel), act, slope, x.numel(), c,
+                                           h * w, y.data_ptr(), _stream()), "act_fwd")
+    return y
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, grad_scale, step):
+    _lib.check(_lib.load().b200gan_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
+                                             beta1, beta2, eps, grad_scale, step.data_ptr(), _stream()), "adam_step")

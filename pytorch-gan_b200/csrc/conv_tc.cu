@@ -1,0 +1,464 @@
+// conv_tc.cu -- tcgen05 TF32 implicit-GEMM convolution (fprop and dgrad) for sm_100a.
+//
+// Hot path of the reference: the big Generator convolutions
+//   Upsample(x2) -> Conv2d(128,128,3,1,1)   dcgan.py:54-55
+//   Upsample(x2) -> Conv2d(128, 64,3,1,1)   dcgan.py:58-59
+// and every other stride-1 convolution with >= 32 input channels (cyclegan/models.py:28,32,75).
+//
+// Formulation.  y[m][k] = sum_taps sum_c A_tap[m][c] * B_tap[k][c], m = output pixel, accumulated in
+// TMEM by tcgen05.mma (kind::tf32, M = 128, N = BN).  No im2col buffer ever exists: the A tile of a
+// tap is a rank-5 TMA box {32 channels, BW, 1, BH, BNn} of the NHWC activation tensor shifted by the
+// tap offset; TMA zero-fills out-of-bounds coordinates, which *is* the zero padding.  The box lands
+// in shared memory as 128 rows x 128 B with the 128-byte swizzle -- exactly the K-major UMMA operand
+// layout.  B tiles come from the packed weight matrix [tap][Cout][Cin] (tf32-rounded at pack time).
+//
+// A nearest x2 upsample in front of a 3x3 conv is folded into four 2x2 "phase" convolutions on the
+// low-resolution input (B200GAN_PACK_TC_*_UP2): the 4x larger upsampled tensor is never written and
+// 2.25x fewer MACs are executed.  The data gradient of that composite runs through the same kernel:
+// 16 taps over a rank-5 phase view {2K, Q/2, 2, P/2, N} of dy.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// thread), warps 2-5 = epilogue (tcgen05.ld -> bias / activation / Dropout2d scale / BatchNorm
+// partial sums -> global).  smem ring of STAGES x (A 16 KB + B BN*128 B), full/empty mbarriers;
+// two CTAs are resident per SM so one CTA's epilogue overlaps the other's main loop.
+#include "tc_common.cuh"
+#include <mutex>
+
+namespace b200gan {
+
+// ---- tensor map encoder ----------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                  const uint32_t *box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return B200GAN_E_CUDA;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]", (int)r,
+              rank, (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+              (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0),
+              (unsigned long long)(rank > 4 ? gd[4] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
+              rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
+    return B200GAN_E_CUDA;
+  }
+  return B200GAN_OK;
+}
+
+// ---- kernel ------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // fp32 elements = 128 bytes = one swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;
+constexpr int TC_MAX_TAPS = 52;
+constexpr int TC_THREADS = 192;
+
+struct TcTap {
+  int16_t dc;  // channel base offset in the A view (selects the w-parity half of a phase view)
+  int8_t dw, da, dh;
+  int8_t pad_[3];
+};
+
+struct TcParams {
+  int32_t tap_begin[5];  // taps of phase z: [tap_begin[z], tap_begin[z+1])
+  TcTap taps[TC_MAX_TAPS];
+  int32_t kout_total;  // rows of the packed B matrix per tap
+  int32_t kchunks;     // contraction channels / 32
+  int32_t bw_log2, bh_log2;  // box width / height (powers of two), BW*BH*BNn = 128
+  int32_t tiles_w, tiles_h;
+  int32_t N, Ho, Wo;         // logical output grid of one phase
+  int64_t out_off[4];        // element offset of a phase's (0,0,0) output pixel
+  int64_t sn, sh, sw;        // output strides in elements
+  int32_t ldk;               // channels of the output tensor (row length)
+  const float *bias;
+  const float *chan_scale;
+  double *stats;
+  int32_t act;
+  float slope;
+  int32_t rtf;
+  float *y;
+};
+
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = upper ? v[i] : v[i + off];
+      float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];  // sum over the 32 lanes of column `lane`
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcParams p) {
+  constexpr int B_BYTES = BN * TC_BK * 4;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *empty = full + STAGES;
+  uint64_t *tmem_full = empty + STAGES;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+  float *red = reinterpret_cast<float *>(tmem_ptr + 2);  // [4][BN][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ph = blockIdx.z;
+  const int ntile = blockIdx.y;
+  const int BW = 1 << p.bw_log2, BH = 1 << p.bh_log2;
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2;
+  const int n0 = tn * (TC_BM >> (p.bw_log2 + p.bh_log2));
+  const int tap0 = p.tap_begin[ph];
+  const int iters = (p.tap_begin[ph + 1] - tap0) * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      int tap = 0, kc = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t *sa = smem + stage * STAGE_BYTES;
+        uint8_t *sb = sa + TC_A_BYTES;
+        const TcTap tp = p.taps[tap0 + tap];
+        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+        tma_load_5d(sa, &tmA, &full[stage], tp.dc + kc * TC_BK, w0 + tp.dw, tp.da, h0 + tp.dh, n0);
+        tma_load_2d(sb, &tmB, &full[stage], kc * TC_BK, (tap0 + tap) * p.kout_total + ntile * BN);
+        if (++kc == p.kchunks) {
+          kc = 0;
+          ++tap;
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+          uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+          umma_tf32(tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp & 3) =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int lw = m & (BW - 1);
+    const int lh = (m >> p.bw_log2) & (BH - 1);
+    const int ln = m >> (p.bw_log2 + p.bh_log2);
+    const int ow = w0 + lw, oh = h0 + lh, on = n0 + ln;
+    const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
+    float *yrow = p.y + p.out_off[ph] + (int64_t)on * p.sn + (int64_t)oh * p.sh + (int64_t)ow * p.sw + ntile * BN;
+    const float *cs = p.chan_scale ? p.chan_scale + (int64_t)on * p.ldk + ntile * BN : nullptr;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float o = v[j];
+        if (p.bias) o += __ldg(p.bias + ntile * BN + c + j);
+        o = apply_act(o, p.act, p.slope);
+        if (cs && valid) o *= __ldg(cs + c + j);
+        if (p.rtf) o = round_tf32(o);
+        v[j] = o;
+      }
+      if (valid) {
+        float4 *dst = reinterpret_cast<float4 *>(yrow + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (p.stats) {
+        float s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = valid ? v[j] : 0.f;
+          s2[j] = v[j] * v[j];
+        }
+        float cs1 = warp_colsum32(v, lane);
+        float cs2 = warp_colsum32(s2, lane);
+        red[(q * BN + c + lane) * 2 + 0] = cs1;
+        red[(q * BN + c + lane) * 2 + 1] = cs2;
+      }
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;
+      if (e < BN) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          a += red[(qq * BN + e) * 2 + 0];
+          b += red[(qq * BN + e) * 2 + 1];
+        }
+        atomicAdd(p.stats + ntile * BN + e, (double)a);
+        atomicAdd(p.stats + p.ldk + ntile * BN + e, (double)b);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<BN>(tmem);
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+static int ilog2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + 4 * BN * 2 * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+// Which passes of which geometries the tcgen05 path takes.
+int tc_supported(const b200gan_conv_geom *g, int pass) {
+  if (g->transposed || g->stride != 1 || g->pad_mode != B200GAN_PAD_ZERO) return 0;
+  if (g->N < 1) return 0;
+  if (pass == 2) return 0;  // weight gradient: wgrad_tc.cu (not yet enabled)
+  const int cin = pass == 0 ? g->C : g->K;   // contraction channels
+  const int cout = pass == 0 ? g->K : g->C;  // produced channels
+  if (cin % 32 != 0 || cout % 64 != 0) return 0;
+  if (g->R * g->S > 49) return 0;
+  if (g->up == 2) {
+    if (!(g->R == 3 && g->S == 3 && g->pad_t == 1 && g->pad_l == 1 && g->pad_b == 1 && g->pad_r == 1)) return 0;
+    if (2 * cin > 32767) return 0;
+  }
+  if (g->pad_t > 100 || g->pad_l > 100 || g->R > 100 || g->S > 100) return 0;
+  return 1;
+}
+
+// Shared by fprop and dgrad.
+//  in      : contracted activation tensor [N][Hi][Wi][Cc] (x for fprop, dy for dgrad)
+//  phase_in: 1 -> `in` is addressed through the phase view {2Cc, Wi/2, 2, Hi/2, N} (dgrad of UP2)
+//  out grid: N x Ho x Wo pixels per phase, written with strides (sn, sh, sw) at out_off[phase]
+static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in, const float *packedB, int Kout,
+                  int nphase, const int *tap_begin, const TcTap *taps, int Ho, int Wo, const int64_t *out_off,
+                  int64_t sn, int64_t sh, int64_t sw, int ldk, const b200gan_epilogue *ep, float *y, cudaStream_t st) {
+  const int BN = (Kout % 128 == 0) ? 128 : 64;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int total_taps = tap_begin[nphase];
+  for (int i = 0; i <= 4; ++i) p.tap_begin[i] = tap_begin[i < nphase ? i : nphase];
+  for (int i = 0; i < total_taps; ++i) p.taps[i] = taps[i];
+  p.kout_total = Kout;
+  p.kchunks = Cc / TC_BK;
+  int bwl = ilog2_ceil(Wo);
+  if (bwl > 7) bwl = 7;
+  int bhl = ilog2_ceil(Ho);
+  if (bhl > 7 - bwl) bhl = 7 - bwl;
+  const int BW = 1 << bwl, BH = 1 << bhl, BNn = TC_BM / (BW * BH);
+  p.bw_log2 = bwl;
+  p.bh_log2 = bhl;
+  p.tiles_w = ceil_div(Wo, BW);
+  p.tiles_h = ceil_div(Ho, BH);
+  p.N = N;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  for (int i = 0; i < 4; ++i) p.out_off[i] = i < nphase ? out_off[i] : 0;
+  p.sn = sn;
+  p.sh = sh;
+  p.sw = sw;
+  p.ldk = ldk;
+  p.bias = ep ? ep->bias : nullptr;
+  p.chan_scale = ep ? ep->chan_scale : nullptr;
+  p.stats = ep ? ep->stats : nullptr;
+  p.act = ep ? ep->act : 0;
+  p.slope = ep ? ep->slope : 0.f;
+  p.rtf = ep ? ep->round_tf32 : 0;
+  p.y = y;
+  B2_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)packedB % 16 == 0) && ((uintptr_t)y % 16 == 0),
+               "tcgen05 conv: pointers must be 16-byte aligned");
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5] = {TC_BK, (uint32_t)BW, 1, (uint32_t)BH, (uint32_t)BNn};
+    if (!phase_in) {
+      dims[0] = Cc; dims[1] = Wi; dims[2] = 1; dims[3] = Hi; dims[4] = N;
+      strides[0] = (uint64_t)Cc * 4;
+      strides[1] = (uint64_t)Wi * Cc * 4;  // size-1 dim: any legal stride
+      strides[2] = (uint64_t)Wi * Cc * 4;
+      strides[3] = (uint64_t)Hi * Wi * Cc * 4;
+    } else {
+      dims[0] = 2 * (uint64_t)Cc; dims[1] = Wi / 2; dims[2] = 2; dims[3] = Hi / 2; dims[4] = N;
+      strides[0] = (uint64_t)2 * Cc * 4;
+      strides[1] = (uint64_t)Wi * Cc * 4;
+      strides[2] = (uint64_t)2 * Wi * Cc * 4;
+      strides[3] = (uint64_t)Hi * Wi * Cc * 4;
+    }
+    if (int e = make_tmap_f32(&tmA, in, 5, dims, strides, box)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Cc, (uint64_t)total_taps * Kout};
+    uint64_t strides[1] = {(uint64_t)Cc * 4};
+    uint32_t box[2] = {TC_BK, (uint32_t)BN};
+    if (int e = make_tmap_f32(&tmB, packedB, 2, dims, strides, box)) return e;
+  }
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)nphase);
+  if (BN == 128) return launch_tc<128, 3>(tmA, tmB, p, grid, st);
+  return launch_tc<64, 4>(tmA, tmB, p, grid, st);
+}
+
+int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
+             cudaStream_t st) {
+  TcTap taps[TC_MAX_TAPS];
+  memset(taps, 0, sizeof(taps));
+  int tap_begin[5] = {0, 0, 0, 0, 0};
+  int64_t out_off[4] = {0, 0, 0, 0};
+  b200gan_epilogue e2;
+  if (ep) {
+    e2 = *ep;
+    // per-sample (InstanceNorm) sums can only be fused when a tile never spans two images
+    if (e2.stats && e2.stats_per_sample) B2_UNSUPPORTED("tcgen05 fprop: per-sample statistics are not fused");
+  }
+  const int64_t K = g->K;
+  if (g->up == 2) {
+    // phase (a,b): out[2i+a][2j+b] = sum_{dr,ds} x[i+a-1+dr][j+b-1+ds] * Wf[a][b][dr][ds]
+    for (int ph = 0; ph < 4; ++ph) {
+      int a = ph >> 1, b = ph & 1;
+      tap_begin[ph] = ph * 4;
+      for (int tp = 0; tp < 4; ++tp) {
+        int dr = tp >> 1, ds = tp & 1;
+        TcTap &t = taps[ph * 4 + tp];
+        t.dc = 0; t.dw = (int8_t)(b - 1 + ds); t.da = 0; t.dh = (int8_t)(a - 1 + dr);
+      }
+      out_off[ph] = ((int64_t)a * g->Q + b) * K;
+    }
+    tap_begin[4] = 16;
+    return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 4, tap_begin, taps, g->H, g->W, out_off,
+                  (int64_t)g->P * g->Q * K, (int64_t)2 * g->Q * K, (int64_t)2 * K, g->K, ep ? &e2 : nullptr, y, st);
+  }
+  int nt = 0;
+  for (int r = 0; r < g->R; ++r)
+    for (int s = 0; s < g->S; ++s) {
+      TcTap &t = taps[nt++];
+      t.dc = 0; t.dw = (int8_t)(s - g->pad_l); t.da = 0; t.dh = (int8_t)(r - g->pad_t);
+    }
+  tap_begin[1] = nt;
+  return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 1, tap_begin, taps, g->P, g->Q, out_off,
+                (int64_t)g->P * g->Q * K, (int64_t)g->Q * K, K, g->K, ep ? &e2 : nullptr, y, st);
+}
+
+int tc_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, float *dx, cudaStream_t st) {
+  TcTap taps[TC_MAX_TAPS];
+  memset(taps, 0, sizeof(taps));
+  int tap_begin[5] = {0, 0, 0, 0, 0};
+  int64_t out_off[4] = {0, 0, 0, 0};
+  const int64_t C = g->C;
+  if (g->up == 2) {
+    // dx[i][j] = sum_{a,b,dr,ds} dy[2(i-(a-1+dr))+a][2(j-(b-1+ds))+b] * Wf[a][b][dr][ds]^T
+    for (int ph = 0; ph < 4; ++ph) {
+      int a = ph >> 1, b = ph & 1;
+      for (int tp = 0; tp < 4; ++tp) {
+        int dr = tp >> 1, ds = tp & 1;
+        TcTap &t = taps[ph * 4 + tp];
+        t.dc = (int16_t)(b * g->K); t.dw = (int8_t)(-(b - 1 + ds)); t.da = (int8_t)a; t.dh = (int8_t)(-(a - 1 + dr));
+      }
+    }
+    tap_begin[1] = 16;
+    return run_tc(dy, g->N, g->P, g->Q, g->K, true, packed, g->C, 1, tap_begin, taps, g->H, g->W, out_off,
+                  (int64_t)g->H * g->W * C, (int64_t)g->W * C, C, g->C, nullptr, dx, st);
+  }
+  int nt = 0;
+  for (int r = 0; r < g->R; ++r)
+    for (int s = 0; s < g->S; ++s) {
+      TcTap &t = taps[nt++];
+      t.dc = 0; t.dw = (int8_t)(g->pad_l - s); t.da = 0; t.dh = (int8_t)(g->pad_t - r);
+    }
+  tap_begin[1] = nt;
+  return run_tc(dy, g->N, g->P, g->Q, g->K, false, packed, g->C, 1, tap_begin, taps, g->H, g->W, out_off,
+                (int64_t)g->H * g->W * C, (int64_t)g->W * C, C, g->C, nullptr, dx, st);
+}
+
+size_t tc_wgrad_workspace_floats(const b200gan_conv_geom *) { return 0; }
+int tc_wgrad(const b200gan_conv_geom *, const float *, const float *, float *, float *, cudaStream_t) {
+  B2_UNSUPPORTED("tcgen05 wgrad not built in this revision");
+}
+
+}  // namespace b200gan

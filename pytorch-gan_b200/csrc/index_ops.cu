@@ -1,0 +1,302 @@
+// index_ops.cu -- shape/index kernels (bit-exact data movement), element-wise activation,
+// epilogue backward and the flat Adam step.  All are streaming HBM-bound passes.
+//
+// Reference modules replaced when they cannot be folded into a neighbouring kernel:
+//   nn.Upsample(scale_factor=2)  dcgan.py:54,58   (nearest: dst -> src = dst // 2)
+//   nn.ZeroPad2d((1,0,1,0))      pix2pix/models.py:78,126  (left & top only)
+//   nn.ReflectionPad2d(k)        cyclegan/models.py:27,31,49,81 (edge pixel not repeated)
+//   nn.LeakyReLU/ReLU/Tanh       dcgan.py:57,63 ...
+//   nn.Dropout / nn.Dropout2d    mask drawn by torch (same RNG stream as the reference), applied here
+//   torch.optim.Adam             dcgan.py:134-135
+#include "common.cuh"
+
+namespace b200gan {
+
+// ---- NCHW <-> NHWC ----------------------------------------------------------------------------
+// per image: [C][HW] <-> [HW][C]: classic 32x32 smem tile transpose. grid (HW/32, C/32, N)
+__global__ void transpose_kernel(const float *__restrict__ x, float *__restrict__ y, int rows, int cols) {
+  // x: [rows][cols] -> y: [cols][rows], per blockIdx.z image
+  __shared__ float tile[32][33];
+  const int64_t img = (int64_t)blockIdx.z * rows * cols;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = x[img + (int64_t)r * cols + c];
+  }
+  __syncthreads();
+  int r = r0 + threadIdx.x;
+  int c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int cc = c0 + i;
+    if (r < rows && cc < cols) y[img + (int64_t)cc * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+static int launch_transpose(const float *x, float *y, int N, int rows, int cols, cudaStream_t st) {
+  if (N == 0 || rows == 0 || cols == 0) return B200GAN_OK;
+  if (rows == 1 || cols == 1) {
+    B2_CUDA(cudaMemcpyAsync(y, x, (size_t)N * rows * cols * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return B200GAN_OK;
+  }
+  B2_CHECK_ARG(N <= 65535 && ceil_div(rows, 32) <= 65535, "transpose: dims too large");
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), N);
+  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(x, y, rows, cols);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+// ---- nearest x2 upsample ---------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t total,
+                                      int H, int W, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int ow = (int)(t % (2 * W));
+    t /= (2 * W);
+    int oh = (int)(t % (2 * H));
+    int n = (int)(t / (2 * H));
+    y[i] = __ldg(x + (((int64_t)n * H + (oh >> 1)) * W + (ow >> 1)) * C + c);
+  }
+}
+__global__ void upsample2x_bwd_kernel(const float *__restrict__ dy, float *__restrict__ dx, int64_t total,
+                                      int H, int W, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int w = (int)(t % W);
+    t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    const float *p = dy + (((int64_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
+    int64_t rs = (int64_t)2 * W * C;
+    dx[i] = (__ldg(p) + __ldg(p + C)) + (__ldg(p + rs) + __ldg(p + rs + C));
+  }
+}
+
+// ---- padding ------------------------------------------------------------------------------------
+__global__ void pad2d_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t total, int H,
+                                 int W, int C, int Ho, int Wo, int pad_t, int pad_l, int mode) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int ow = (int)(t % Wo);
+    t /= Wo;
+    int oh = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    int ih = oh - pad_t, iw = ow - pad_l;
+    float v = 0.f;
+    if (mode == B200GAN_PAD_REFLECT) {
+      ih = reflect_idx(ih, H);
+      iw = reflect_idx(iw, W);
+      v = __ldg(x + (((int64_t)n * H + ih) * W + iw) * C + c);
+    } else if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      v = __ldg(x + (((int64_t)n * H + ih) * W + iw) * C + c);
+    }
+    y[i] = v;
+  }
+}
+// gradient: zero pad -> crop; reflect -> each input pixel sums the (<= 4) padded pixels that mirror
+// onto it.  Gather formulation (deterministic, no atomics).
+__global__ void pad2d_bwd_kernel(const float *__restrict__ dy, float *__restrict__ dx, int64_t total, int H,
+                                 int W, int C, int Ho, int Wo, int pad_t, int pad_l, int pad_b, int pad_r,
+                                 int mode) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int w = (int)(t % W);
+    t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    const float *base = dy + (int64_t)n * Ho * Wo * C + c;
+    // candidate padded rows mapping onto h: h+pad_t (interior), pad_t-h (top mirror, h in [1,pad_t]),
+    // pad_t + 2(H-1) - h (bottom mirror, H-1-h in [1,pad_b])
+    int rows[3], nr = 0, cols[3], nc = 0;
+    rows[nr++] = h + pad_t;
+    cols[nc++] = w + pad_l;
+    if (mode == B200GAN_PAD_REFLECT) {
+      if (h >= 1 && h <= pad_t) rows[nr++] = pad_t - h;
+      if (H - 1 - h >= 1 && H - 1 - h <= pad_b) rows[nr++] = pad_t + 2 * (H - 1) - h;
+      if (w >= 1 && w <= pad_l) cols[nc++] = pad_l - w;
+      if (W - 1 - w >= 1 && W - 1 - w <= pad_r) cols[nc++] = pad_l + 2 * (W - 1) - w;
+    }
+    float s = 0.f;
+    for (int a = 0; a < nr; ++a)
+      for (int b = 0; b < nc; ++b) s += __ldg(base + ((int64_t)rows[a] * Wo + cols[b]) * C);
+    dx[i] = s;
+  }
+}
+
+// ---- activation (+ mask) --------------------------------------------------------------------------
+__global__ void act_fwd_kernel(const float *__restrict__ x, const float *__restrict__ mask, int mask_pc,
+                               int act, float slope, int64_t n, int C, int64_t HW, float *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = apply_act(__ldg(x + i), act, slope);
+    if (mask) {
+      if (mask_pc) {
+        int c = (int)(i % C);
+        int64_t img = i / ((int64_t)C * HW);
+        v *= __ldg(mask + img * C + c);
+      } else {
+        v *= __ldg(mask + i);
+      }
+    }
+    y[i] = v;
+  }
+}
+
+__global__ void epilogue_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y,
+                                    const float *__restrict__ chan_scale, int act, float slope, int64_t n,
+                                    int K, int64_t PQ, int rtf, float *__restrict__ dz) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float d = __ldg(dy + i);
+    float cs = 1.f;
+    if (chan_scale) {
+      int k = (int)(i % K);
+      int64_t img = i / ((int64_t)K * PQ);
+      cs = __ldg(chan_scale + img * K + k);
+      d *= cs;
+    }
+    if (act != B200GAN_ACT_NONE) {
+      // y = cs * act(z): recover act(z) for the derivative.  cs == 0 (dropped channel) gives d == 0
+      // already; for LReLU/ReLU only the sign of y matters (cs >= 0).
+      float yv = __ldg(y + i);
+      if (chan_scale && (act == B200GAN_ACT_TANH || act == B200GAN_ACT_SIGMOID))
+        yv = cs != 0.f ? yv / cs : 0.f;
+      d *= act_grad_from_out(yv, act, slope);
+    }
+    dz[i] = rtf ? round_tf32(d) : d;
+  }
+}
+
+// ---- Adam ---------------------------------------------------------------------------------------------
+// torch.optim.Adam (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  Step count lives on the device.
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                            float *__restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float gscale, const float *__restrict__ step) {
+  float t = *step + 1.f;
+  float bc1 = 1.f - powf(b1, t);
+  float bc2 = 1.f - powf(b2, t);
+  float step_size = lr / bc1;
+  float bc2_sqrt = sqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+__global__ void adam_step_inc_kernel(float *step) { *step += 1.f; }
+
+static unsigned stream_blocks(int64_t n) {
+  int64_t b = ceil_div64(n, 256);
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace b200gan
+
+using namespace b200gan;
+
+extern "C" int b200gan_nchw_to_nhwc(const float *x, float *y, int32_t N, int32_t C, int32_t HW, void *stream) {
+  B2_CHECK_ARG(x && y, "nchw_to_nhwc: null pointer");
+  return launch_transpose(x, y, N, C, HW, as_stream(stream));
+}
+extern "C" int b200gan_nhwc_to_nchw(const float *x, float *y, int32_t N, int32_t C, int32_t HW, void *stream) {
+  B2_CHECK_ARG(x && y, "nhwc_to_nchw: null pointer");
+  return launch_transpose(x, y, N, HW, C, as_stream(stream));
+}
+
+extern "C" int b200gan_upsample2x_fwd(const float *x, float *y, int32_t N, int32_t H, int32_t W, int32_t C,
+                                      void *stream) {
+  B2_CHECK_ARG(x && y, "upsample2x_fwd: null pointer");
+  int64_t total = (int64_t)N * 4 * H * W * C;
+  if (total == 0) return B200GAN_OK;
+  upsample2x_fwd_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, total, H, W, C);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+extern "C" int b200gan_upsample2x_bwd(const float *dy, float *dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                                      void *stream) {
+  B2_CHECK_ARG(dy && dx, "upsample2x_bwd: null pointer");
+  int64_t total = (int64_t)N * H * W * C;
+  if (total == 0) return B200GAN_OK;
+  upsample2x_bwd_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(dy, dx, total, H, W, C);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_pad2d_fwd(const float *x, float *y, int32_t N, int32_t H, int32_t W, int32_t C,
+                                 int32_t pad_t, int32_t pad_l, int32_t pad_b, int32_t pad_r, int32_t mode,
+                                 void *stream) {
+  B2_CHECK_ARG(x && y, "pad2d_fwd: null pointer");
+  B2_CHECK_ARG(mode != B200GAN_PAD_REFLECT || (pad_t < H && pad_b < H && pad_l < W && pad_r < W),
+               "pad2d_fwd: reflection pad must be smaller than the input");
+  int Ho = H + pad_t + pad_b, Wo = W + pad_l + pad_r;
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  if (total == 0) return B200GAN_OK;
+  pad2d_fwd_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, total, H, W, C, Ho, Wo, pad_t,
+                                                                         pad_l, mode);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+extern "C" int b200gan_pad2d_bwd(const float *dy, float *dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                                 int32_t pad_t, int32_t pad_l, int32_t pad_b, int32_t pad_r, int32_t mode,
+                                 void *stream) {
+  B2_CHECK_ARG(dy && dx, "pad2d_bwd: null pointer");
+  int Ho = H + pad_t + pad_b, Wo = W + pad_l + pad_r;
+  int64_t total = (int64_t)N * H * W * C;
+  if (total == 0) return B200GAN_OK;
+  pad2d_bwd_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(dy, dx, total, H, W, C, Ho, Wo, pad_t,
+                                                                         pad_l, pad_b, pad_r, mode);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_act_fwd(const float *x, const float *mask, int32_t mask_per_channel, int32_t act,
+                               float slope, int64_t n, int32_t C, int64_t HW, float *y, void *stream) {
+  B2_CHECK_ARG(x && y, "act_fwd: null pointer");
+  if (n == 0) return B200GAN_OK;
+  act_fwd_kernel<<<stream_blocks(n), 256, 0, as_stream(stream)>>>(x, mask, mask_per_channel, act, slope, n, C,
+                                                                   HW, y);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_epilogue_bwd(const float *dy, const float *y, const float *chan_scale, int32_t act,
+                                    float slope, int64_t n, int32_t K, int64_t PQ, int32_t round_tf32_,
+                                    float *dz, void *stream) {
+  B2_CHECK_ARG(dy && dz, "epilogue_bwd: null pointer");
+  B2_CHECK_ARG(act == B200GAN_ACT_NONE || y != nullptr, "epilogue_bwd: activation needs saved output");
+  if (n == 0) return B200GAN_OK;
+  epilogue_bwd_kernel<<<stream_blocks(n), 256, 0, as_stream(stream)>>>(dy, y, chan_scale, act, slope, n, K, PQ,
+                                                                        round_tf32_, dz);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
+                                 float beta1, float beta2, float eps, float grad_scale, float *step,
+                                 void *stream) {
+  B2_CHECK_ARG(p && g && m && v && step, "adam_step: null pointer");
+  if (n > 0) {
+    adam_kernel<<<stream_blocks(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                 grad_scale, step);
+    B2_LAUNCH_CHECK();
+  }
+  adam_step_inc_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
