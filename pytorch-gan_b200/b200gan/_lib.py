@@ -94,7 +94,12 @@ def load():
     return lib
 
 
+CALLS = 0  # number of C-ABI launches issued by this process (each is >= 1 CUDA kernel)
+
+
 def check(rc, what=""):
+    global CALLS
+    CALLS += 1
     if rc != 0:
         msg = load().b200gan_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"libb200gan {what} failed (code {rc}): {msg}")

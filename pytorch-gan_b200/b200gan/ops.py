@@ -5,6 +5,7 @@ Activations are torch tensors of logical shape [N, C, H, W] whose memory is NHWC
 PyTorch is used for device memory (caching allocator), streams and tensor plumbing only.
 """
 import ctypes
+import os
 
 import torch
 
@@ -16,7 +17,7 @@ CL = torch.channels_last
 
 class Config:
     """Global switches. `algo`: 'auto' (tcgen05 where the geometry qualifies) or 'simt'."""
-    algo = "auto"
+    algo = os.environ.get("B200GAN_ALGO", "auto")
     weight_cache = True
 
 
@@ -53,6 +54,8 @@ def to_cl(x):
         x = x.contiguous()
     n, c, h, w = x.shape
     y = empty_cl(n, c, h, w, x.device)
+    if x.numel() == 0:
+        return y
     _lib.check(_lib.load().b200gan_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), n, c, h * w, _stream()), "nchw_to_nhwc")
     return y
 
@@ -66,6 +69,8 @@ def to_nchw(x):
         return x.contiguous()
     n, c, h, w = x.shape
     y = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    if x.numel() == 0:
+        return y
     _lib.check(_lib.load().b200gan_nhwc_to_nchw(x.data_ptr(), y.data_ptr(), n, c, h * w, _stream()), "nhwc_to_nchw")
     return y
 
@@ -111,6 +116,8 @@ def pack_weights(g, w, kind):
 def conv_fprop(g, x, packed, algo, bias=None, act=ACT_NONE, slope=0.0, chan_scale=None, stats=None,
                stats_per_sample=False, round_tf32=False):
     y = empty_cl(g.N, g.K, g.P, g.Q, x.device)
+    if g.N == 0:
+        return y
     ep = Epilogue()
     ep.bias, ep.act, ep.slope = _ptr(bias), act, slope
     ep.chan_scale, ep.stats = _ptr(chan_scale), _ptr(stats)

@@ -296,11 +296,13 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
   return B200GAN_OK;
 }
 
+int tc_wgrad_supported(const b200gan_conv_geom *g);  // wgrad_tc.cu
+
 // Which passes of which geometries the tcgen05 path takes.
 int tc_supported(const b200gan_conv_geom *g, int pass) {
   if (g->transposed || g->stride != 1 || g->pad_mode != B200GAN_PAD_ZERO) return 0;
   if (g->N < 1) return 0;
-  if (pass == 2) return 0;  // weight gradient: wgrad_tc.cu (not yet enabled)
+  if (pass == 2) return tc_wgrad_supported(g);  // weight gradient: wgrad_tc.cu
   const int cin = pass == 0 ? g->C : g->K;   // contraction channels
   const int cout = pass == 0 ? g->K : g->C;  // produced channels
   if (cin % 32 != 0 || cout % 64 != 0) return 0;
@@ -454,11 +456,6 @@ int tc_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, f
   tap_begin[1] = nt;
   return run_tc(dy, g->N, g->P, g->Q, g->K, false, packed, g->C, 1, tap_begin, taps, g->H, g->W, out_off,
                 (int64_t)g->H * g->W * C, (int64_t)g->W * C, C, g->C, nullptr, dx, st);
-}
-
-size_t tc_wgrad_workspace_floats(const b200gan_conv_geom *) { return 0; }
-int tc_wgrad(const b200gan_conv_geom *, const float *, const float *, float *, float *, cudaStream_t) {
-  B2_UNSUPPORTED("tcgen05 wgrad not built in this revision");
 }
 
 }  // namespace b200gan

@@ -1,0 +1,359 @@
+// wgrad_tc.cu -- tcgen05 TF32 weight gradient of the stride-1 convolutions (sm_100a).
+//
+// dW[tap][k][c] = sum over output pixels o of  dy[o][k] * x[o + offset(tap)][c]
+// (reference: autograd of nn.Conv2d, dcgan.py:168,182 -> cudnnConvolutionBackwardFilter).
+//
+// As a GEMM the contraction runs over PIXELS, so both operands are "MN-major" in UMMA terms: a TMA
+// box {32 channels, BW, 1, BH, 1} (32 pixels) lands in shared memory as 32 rows x 128 B (128-byte
+// swizzle), i.e. the canonical MN-major SW128 layout ((32 ch contiguous) x (8 pixel rows per atom));
+// one 32-channel chunk per box, chunks LBO bytes apart.  The operand with a multiple of 128 channels is
+// A (M = 128), the other is B (N = 64/128).  Zero padding = TMA out-of-bounds fill on the shifted x box.
+// The upsample-folded convolution (dcgan.py:54-55,58-59) contributes 16 (phase, tap) jobs that read dy
+// through the phase view {2K, Q/2, 2, P/2, N}; a second kernel folds them back into the 3x3 filter.
+//
+// Parallelisation: grid = (pixel splits, jobs, M-tiles x N-tiles).  Every CTA accumulates its pixel
+// range in TMEM and stores a partial tile; wgrad_reduce_kernel sums the partials in a fixed order
+// (deterministic, no atomics) while converting to the parameter layout [K][C][R][S].
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace b200gan {
+
+constexpr int WG_PIX = 32;            // pixels (GEMM-K) per pipeline stage
+constexpr int WG_CHUNK_BYTES = WG_PIX * 128;  // one 32-channel chunk of one stage
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_JOBS = 52;
+
+struct WgJob {
+  int16_t dc;          // dy channel base (phase view: b*K)
+  int8_t da;           // dy phase row
+  int8_t dw, dh;       // x shift
+  int8_t pad_[3];
+};
+
+struct WgParams {
+  WgJob jobs[WG_MAX_JOBS];
+  int32_t njobs;
+  int32_t bw_log2, bh_log2;       // 32-pixel box = BW x BH
+  int32_t tiles_w, tiles_h, N;    // pixel tiles per image
+  int32_t tiles_total, tiles_per_split;
+  int32_t x_is_a;                 // 1: A = x (M' = Cin), B = dy (N' = Cout); 0: A = dy, B = x
+  int32_t mtiles, ntiles;         // tiles of the (M', N') output
+  int32_t ldn;                    // N' total (row length of a partial matrix)
+  int32_t mtotal;                 // M' total
+  float *partial;                 // [split][job][M'][N']
+  uint32_t lbo, sbo;              // UMMA descriptor byte offsets (chunk stride, 8-row group stride)
+};
+
+template <int NB, int STAGES>
+__global__ void __launch_bounds__(WG_THREADS, 2)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                const __grid_constant__ WgParams p) {
+  constexpr int A_BYTES = 4 * WG_CHUNK_BYTES;            // 128 channels
+  constexpr int B_BYTES = (NB / 32) * WG_CHUNK_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *empty = full + STAGES;
+  uint64_t *tmem_full = empty + STAGES;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, job = blockIdx.y;
+  const int mt = blockIdx.z / p.ntiles, nt = blockIdx.z % p.ntiles;
+  const int t_begin = split * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.tiles_total) t_end = p.tiles_total;
+  const int iters = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<NB>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const WgJob jb = p.jobs[job];
+      const CUtensorMap *mapA = p.x_is_a ? &tmX : &tmY;
+      const CUtensorMap *mapB = p.x_is_a ? &tmY : &tmX;
+      // per-operand coordinate recipe: x is shifted by the tap, dy sits in its phase
+      const int a_dc = p.x_is_a ? 0 : jb.dc, a_dw = p.x_is_a ? jb.dw : 0, a_da = p.x_is_a ? 0 : jb.da,
+                a_dh = p.x_is_a ? jb.dh : 0;
+      const int b_dc = p.x_is_a ? jb.dc : 0, b_dw = p.x_is_a ? 0 : jb.dw, b_da = p.x_is_a ? jb.da : 0,
+                b_dh = p.x_is_a ? 0 : jb.dh;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        int t = t_begin + it;
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t *sa = smem + stage * STAGE_BYTES;
+        uint8_t *sb = sa + A_BYTES;
+        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_5d(sa + c * WG_CHUNK_BYTES, mapA, &full[stage], a_dc + (mt * 4 + c) * 32, w0 + a_dw, a_da,
+                      h0 + a_dh, n);
+#pragma unroll
+        for (int c = 0; c < NB / 32; ++c)
+          tma_load_5d(sb + c * WG_CHUNK_BYTES, mapB, &full[stage], b_dc + (nt * (NB / 32) + c) * 32, w0 + b_dw, b_da,
+                      h0 + b_dh, n);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, NB, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 8; ++k) {
+          // 8 pixel rows = one swizzle atom (1024 B) per K step; channel chunks are LBO = 4096 B apart
+          uint64_t da = umma_desc_sw128(sa + k * 1024, p.lbo, p.sbo);
+          uint64_t db = umma_desc_sw128(sb + k * 1024, p.lbo, p.sbo);
+          umma_tf32(tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // row of the 128 x NB tile
+    float *dst = p.partial + (((int64_t)split * p.njobs + job) * p.mtotal + (mt * 128 + m)) * p.ldn + nt * NB;
+    if (iters > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < NB; c += 32) {
+      float v[32];
+      if (iters > 0) {
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      float4 *d4 = reinterpret_cast<float4 *>(dst + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<NB>(tmem);
+  }
+}
+
+// dw[k][c][r][s] = sum_splits sum_{jobs contributing to (r,s)} partial[split][job][m'][n'],
+// (m', n') = (c, k) if x_is_a else (k, c).
+struct WgReduceP {
+  int32_t K, C, R, S, nsplits, njobs, x_is_a, up2;
+  int32_t mtotal, ldn;
+};
+__device__ __forceinline__ bool up2_contrib(int r, int a, int d) {
+  // r in Rset(a,d): Rset(0,0)={0} Rset(0,1)={1,2} Rset(1,0)={0,1} Rset(1,1)={2}
+  if (a == 0) return d == 0 ? r == 0 : r >= 1;
+  return d == 0 ? r <= 1 : r == 2;
+}
+__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, WgReduceP p) {
+  int64_t total = (int64_t)p.K * p.C * p.R * p.S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // iterate with c fastest so that reads of partial[..][k][c] (or [c][k]) stay reasonably coalesced
+    int c = (int)(i % p.C);
+    int64_t t = i / p.C;
+    int k = (int)(t % p.K);
+    t /= p.K;
+    int s = (int)(t % p.S), r = (int)(t / p.S);
+    int64_t elem = p.x_is_a ? (int64_t)c * p.ldn + k : (int64_t)k * p.ldn + c;
+    int64_t job_stride = (int64_t)p.mtotal * p.ldn;
+    float acc = 0.f;
+    for (int sp = 0; sp < p.nsplits; ++sp) {
+      const float *base = partial + (int64_t)sp * p.njobs * job_stride + elem;
+      if (!p.up2) {
+        acc += __ldg(base + (int64_t)(r * p.S + s) * job_stride);
+      } else {
+        for (int j = 0; j < 16; ++j) {
+          int ph = j >> 2, tp = j & 3;
+          if (up2_contrib(r, ph >> 1, tp >> 1) && up2_contrib(s, ph & 1, tp & 1)) acc += __ldg(base + j * job_stride);
+        }
+      }
+    }
+    dw[(((int64_t)k * p.C + c) * p.R + r) * p.S + s] = acc;
+  }
+}
+
+// ---- host -------------------------------------------------------------------------------------------
+static int ilog2c(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+struct WgPlan {
+  int x_is_a, NB, mtiles, ntiles, mtotal, ldn, njobs, bwl, bhl, tiles_w, tiles_h, tiles_total, nsplits, tps, Ho, Wo;
+};
+
+static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
+  if (g->transposed || g->stride != 1 || g->pad_mode != B200GAN_PAD_ZERO || g->N < 1) return false;
+  if (g->C % 32 || g->K % 32) return false;
+  const bool up2 = g->up == 2;
+  if (up2 && !(g->R == 3 && g->S == 3 && g->pad_t == 1 && g->pad_l == 1 && g->pad_b == 1 && g->pad_r == 1)) return false;
+  if (g->R * g->S > WG_MAX_JOBS || g->pad_t > 100 || g->pad_l > 100) return false;
+  // A = the operand with a multiple of 128 channels; B = the other (multiple of 64)
+  if (g->K % 128 == 0 && g->C % 64 == 0) pl.x_is_a = 0;
+  else if (g->C % 128 == 0 && g->K % 64 == 0) pl.x_is_a = 1;
+  else return false;
+  const int mch = pl.x_is_a ? g->C : g->K, nch = pl.x_is_a ? g->K : g->C;
+  pl.NB = nch % 128 == 0 ? 128 : 64;
+  pl.mtotal = mch;
+  pl.ldn = nch;
+  pl.mtiles = mch / 128;
+  pl.ntiles = nch / pl.NB;
+  pl.njobs = up2 ? 16 : g->R * g->S;
+  pl.Ho = up2 ? g->H : g->P;  // pixel grid the contraction runs over (low-res grid for the fold)
+  pl.Wo = up2 ? g->W : g->Q;
+  pl.bwl = ilog2c(pl.Wo);
+  if (pl.bwl > 5) pl.bwl = 5;
+  pl.bhl = ilog2c(pl.Ho);
+  if (pl.bhl > 5 - pl.bwl) pl.bhl = 5 - pl.bwl;
+  pl.tiles_w = ceil_div(pl.Wo, 1 << pl.bwl);
+  pl.tiles_h = ceil_div(pl.Ho, 1 << pl.bhl);
+  int64_t tt = (int64_t)g->N * pl.tiles_w * pl.tiles_h;
+  if (tt > (1 << 30)) return false;
+  pl.tiles_total = (int)tt;
+  int ctas_per_split = pl.njobs * pl.mtiles * pl.ntiles;
+  int ns = (2 * 148 + ctas_per_split - 1) / ctas_per_split;
+  int max_ns = pl.tiles_total / 8;
+  if (max_ns < 1) max_ns = 1;
+  if (ns > max_ns) ns = max_ns;
+  if (ns < 1) ns = 1;
+  pl.tps = ceil_div(pl.tiles_total, ns);
+  pl.nsplits = ceil_div(pl.tiles_total, pl.tps);
+  return true;
+}
+
+int tc_wgrad_supported(const b200gan_conv_geom *g) {
+  WgPlan pl;
+  return wg_plan(g, pl) ? 1 : 0;
+}
+
+size_t tc_wgrad_workspace_floats(const b200gan_conv_geom *g) {
+  WgPlan pl;
+  if (!wg_plan(g, pl)) return 0;
+  return (size_t)pl.nsplits * pl.njobs * pl.mtotal * pl.ldn;
+}
+
+template <int NB, int STAGES>
+static int launch_wg(const CUtensorMap &tmX, const CUtensorMap &tmY, const WgParams &p, dim3 grid, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (4 + NB / 32) * WG_CHUNK_BYTES + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  wgrad_tc_kernel<NB, STAGES><<<grid, WG_THREADS, SMEM, st>>>(tmX, tmY, p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float *dw, float *ws, cudaStream_t st) {
+  WgPlan pl;
+  if (!wg_plan(g, pl)) B2_UNSUPPORTED("tcgen05 wgrad: geometry not supported");
+  B2_CHECK_ARG(ws != nullptr, "tcgen05 wgrad: workspace required");
+  B2_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)ws % 16 == 0),
+               "tcgen05 wgrad: pointers must be 16-byte aligned");
+  const bool up2 = g->up == 2;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.njobs = pl.njobs;
+  if (up2) {
+    for (int ph = 0; ph < 4; ++ph)
+      for (int tp = 0; tp < 4; ++tp) {
+        int a = ph >> 1, b = ph & 1, dr = tp >> 1, ds = tp & 1;
+        WgJob &j = p.jobs[ph * 4 + tp];
+        j.dc = (int16_t)(b * g->K); j.da = (int8_t)a; j.dh = (int8_t)(a - 1 + dr); j.dw = (int8_t)(b - 1 + ds);
+      }
+  } else {
+    for (int r = 0; r < g->R; ++r)
+      for (int s = 0; s < g->S; ++s) {
+        WgJob &j = p.jobs[r * g->S + s];
+        j.dc = 0; j.da = 0; j.dh = (int8_t)(r - g->pad_t); j.dw = (int8_t)(s - g->pad_l);
+      }
+  }
+  p.bw_log2 = pl.bwl; p.bh_log2 = pl.bhl;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.N = g->N;
+  p.tiles_total = pl.tiles_total; p.tiles_per_split = pl.tps;
+  p.x_is_a = pl.x_is_a; p.mtiles = pl.mtiles; p.ntiles = pl.ntiles; p.ldn = pl.ldn; p.mtotal = pl.mtotal;
+  p.partial = ws;
+  p.lbo = WG_CHUNK_BYTES;
+  p.sbo = 1024;
+  if (const char *v = getenv("B200GAN_WG_VARIANT")) {  // bring-up switch for the MN-major descriptor fields
+    if (v[0] == '1') { p.lbo = 1024; p.sbo = WG_CHUNK_BYTES; }
+  }
+
+  CUtensorMap tmX, tmY;
+  const uint32_t box[5] = {32, (uint32_t)(1 << pl.bwl), 1, (uint32_t)(1 << pl.bhl), 1};
+  {
+    uint64_t dims[5] = {(uint64_t)g->C, (uint64_t)g->W, 1, (uint64_t)g->H, (uint64_t)g->N};
+    uint64_t strides[4] = {(uint64_t)g->C * 4, (uint64_t)g->W * g->C * 4, (uint64_t)g->W * g->C * 4,
+                           (uint64_t)g->H * g->W * g->C * 4};
+    if (int e = make_tmap_f32(&tmX, x, 5, dims, strides, box)) return e;
+  }
+  {
+    uint64_t dims[5], strides[4];
+    const uint64_t K = g->K, P = g->P, Q = g->Q;
+    if (!up2) {
+      dims[0] = K; dims[1] = Q; dims[2] = 1; dims[3] = P; dims[4] = g->N;
+      strides[0] = K * 4; strides[1] = Q * K * 4; strides[2] = Q * K * 4; strides[3] = P * Q * K * 4;
+    } else {
+      dims[0] = 2 * K; dims[1] = Q / 2; dims[2] = 2; dims[3] = P / 2; dims[4] = g->N;
+      strides[0] = 2 * K * 4; strides[1] = Q * K * 4; strides[2] = 2 * Q * K * 4; strides[3] = P * Q * K * 4;
+    }
+    if (int e = make_tmap_f32(&tmY, dy, 5, dims, strides, box)) return e;
+  }
+  dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
+  int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, p, grid, st) : launch_wg<64, 4>(tmX, tmY, p, grid, st);
+  if (rc) return rc;
+  WgReduceP rp;
+  rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.nsplits = pl.nsplits; rp.njobs = pl.njobs;
+  rp.x_is_a = pl.x_is_a; rp.up2 = up2 ? 1 : 0; rp.mtotal = pl.mtotal; rp.ldn = pl.ldn;
+  int64_t total = (int64_t)g->K * g->C * g->R * g->S;
+  unsigned blocks = (unsigned)(ceil_div64(total, 256) > 2368 ? 2368 : ceil_div64(total, 256));
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, rp);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+}  // namespace b200gan

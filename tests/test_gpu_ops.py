@@ -1,0 +1,314 @@
+"""GPU parity tests (-m gpu): every CUDA kernel, through the C ABI, against (a) stock torch fp32 on
+the same device (cuDNN with TF32 disabled = the reference's own operator path at full precision),
+(b) the golden vectors produced by the reference on CPU, (c) size-independent properties.
+
+Tolerances: 1e-3 norm-relative for floating point (BASELINE.json north star); exact equality
+(torch.equal) for shape / index ops.
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _mods():
+    from b200gan import nn as bnn
+    return bnn
+
+
+def _cl(x):
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+CONV_CASES = [  # cin, cout, k, stride, pad, H, W, N   -- every geometry of SURVEY.md section 0.6
+    (1, 16, 3, 2, 1, 64, 64, 4),     # dcgan D block 1
+    (16, 32, 3, 2, 1, 32, 32, 4),
+    (64, 128, 3, 2, 1, 8, 8, 4),
+    (64, 1, 3, 1, 1, 32, 32, 3),     # dcgan G output conv (small-K kernel)
+    (128, 3, 4, 1, 1, 17, 17, 2),    # pix2pix final conv geometry
+    (3, 64, 4, 2, 1, 32, 32, 2),     # pix2pix down1
+    (6, 64, 4, 2, 1, 16, 16, 2),
+    (3, 8, 7, 1, 0, 22, 22, 2),      # cyclegan 7x7 (after reflection pad)
+    (32, 32, 3, 1, 0, 10, 10, 2),    # residual block conv
+    (5, 7, 3, 1, 1, 9, 11, 3),       # odd everything
+    (64, 64, 3, 1, 1, 16, 16, 2),    # tensor-core eligible
+    (128, 128, 3, 1, 1, 32, 32, 2),
+    (128, 64, 3, 1, 1, 24, 20, 3),   # tensor-core with ragged tiles
+    (256, 256, 3, 1, 0, 18, 18, 1),  # cyclegan residual conv on a padded map
+    (64, 128, 7, 1, 3, 16, 16, 1),
+]
+
+
+@pytest.mark.parametrize("algo", ["simt", "auto"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "c%d_k%d_%dx%ds%dp%d_%dx%d" % (c[0], c[1], c[2], c[2], c[3], c[4], c[5], c[6]))
+def test_conv2d_fwd_bwd(case, algo):
+    import b200gan
+    cin, cout, k, s, p, h, w, n = case
+    prev = b200gan.Config.algo
+    if algo == "auto" and prev == "simt":
+        pytest.skip("B200GAN_ALGO=simt")
+    b200gan.Config.algo = algo
+    try:
+        torch.manual_seed(1)
+        ref = torch.nn.Conv2d(cin, cout, k, s, p).cuda()
+        ours = _mods().Conv2d(cin, cout, k, s, p).cuda()
+        ours.load_state_dict(ref.state_dict())
+        x = torch.randn(n, cin, h, w, device="cuda")
+        xr = x.clone().requires_grad_(True)
+        xo = _cl(x).clone().requires_grad_(True)
+        yr = ref(xr)
+        yo = ours(xo)
+        assert yo.shape == yr.shape
+        assert rel_err(yo, yr) < TOL
+        gy = torch.randn_like(yr)
+        yr.backward(gy)
+        yo.backward(_cl(gy))
+        assert rel_err(xo.grad, xr.grad) < TOL
+        assert rel_err(ours.weight.grad, ref.weight.grad) < TOL
+        assert rel_err(ours.bias.grad, ref.bias.grad) < TOL
+    finally:
+        b200gan.Config.algo = prev
+
+
+@pytest.mark.parametrize("case", [(6, 4, 5, 6, 2), (512, 64, 2, 2, 2), (64, 32, 8, 8, 3), (128, 64, 16, 16, 2)])
+def test_conv_transpose2d_fwd_bwd(case):
+    cin, cout, h, w, n = case
+    torch.manual_seed(2)
+    ref = torch.nn.ConvTranspose2d(cin, cout, 4, 2, 1, bias=False).cuda()
+    ours = _mods().ConvTranspose2d(cin, cout, 4, 2, 1, bias=False).cuda()
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(n, cin, h, w, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    xo = _cl(x).clone().requires_grad_(True)
+    yr, yo = ref(xr), ours(xo)
+    assert yo.shape == yr.shape == (n, cout, 2 * h, 2 * w)
+    assert rel_err(yo, yr) < TOL
+    gy = torch.randn_like(yr)
+    yr.backward(gy)
+    yo.backward(_cl(gy))
+    assert rel_err(xo.grad, xr.grad) < TOL
+    assert rel_err(ours.weight.grad, ref.weight.grad) < TOL
+
+
+def test_conv_golden_vectors_from_torch_cpu(golden_dir):
+    """Fixtures written by oracle/make_golden.py (stock torch CPU) -- forward, dx, dw, db."""
+    bnn = _mods()
+    for c in torch.load(os.path.join(golden_dir, "ops_conv.pt"), weights_only=False):
+        cls = bnn.ConvTranspose2d if c["transposed"] else bnn.Conv2d
+        w = c["w"]
+        cin, cout = (w.shape[0], w.shape[1]) if c["transposed"] else (w.shape[1], w.shape[0])
+        m = cls(cin, cout, w.shape[2], c["stride"], c["pad"]).cuda()
+        with torch.no_grad():
+            m.weight.copy_(w)
+            m.bias.copy_(c["b"])
+        x = c["x"].cuda().requires_grad_(True)
+        y = m(x)
+        assert rel_err(y, c["y"]) < TOL, c["name"]
+        y.backward(c["gy"].cuda())
+        assert rel_err(x.grad, c["gx"]) < TOL, c["name"]
+        assert rel_err(m.weight.grad, c["gw"]) < TOL, c["name"]
+        assert rel_err(m.bias.grad, c["gb"]) < TOL, c["name"]
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n", [(128, 128, 16, 16, 4), (128, 64, 32, 32, 2), (64, 64, 8, 8, 3),
+                                            (32, 16, 6, 5, 2)])
+def test_upsample_conv_folded(cin, cout, h, w, n):
+    """Upsample(x2) -> Conv3x3 inside a Sequential: the 4-phase fold (tcgen05) or the gather (SIMT)."""
+    bnn = _mods()
+    torch.manual_seed(3)
+    ref = torch.nn.Sequential(torch.nn.Upsample(scale_factor=2), torch.nn.Conv2d(cin, cout, 3, 1, 1)).cuda()
+    ours = bnn.Sequential(bnn.Upsample(scale_factor=2), bnn.Conv2d(cin, cout, 3, 1, 1)).cuda()
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(n, cin, h, w, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    xo = x.clone().requires_grad_(True)
+    yr, yo = ref(xr), ours(xo)
+    assert yo.shape == yr.shape and yo.is_contiguous()
+    assert rel_err(yo, yr) < TOL
+    gy = torch.randn_like(yr)
+    yr.backward(gy)
+    yo.backward(gy)
+    assert rel_err(xo.grad, xr.grad) < TOL
+    assert rel_err(ours[1].weight.grad, ref[1].weight.grad) < TOL
+    assert rel_err(ours[1].bias.grad, ref[1].bias.grad) < TOL
+
+
+def test_padded_convs_in_sequential():
+    """ReflectionPad2d(3) -> Conv7x7 (cyclegan/models.py:49-50) and Upsample -> ZeroPad2d((1,0,1,0)) ->
+    Conv4x4 p1 -> Tanh (pix2pix/models.py:76-81)."""
+    bnn = _mods()
+    torch.manual_seed(4)
+    for ref, ours, shape in [
+        (torch.nn.Sequential(torch.nn.ReflectionPad2d(3), torch.nn.Conv2d(3, 16, 7), torch.nn.InstanceNorm2d(16),
+                             torch.nn.ReLU(inplace=True)),
+         bnn.Sequential(bnn.ReflectionPad2d(3), bnn.Conv2d(3, 16, 7), bnn.InstanceNorm2d(16), bnn.ReLU(inplace=True)),
+         (2, 3, 20, 20)),
+        (torch.nn.Sequential(torch.nn.Upsample(scale_factor=2), torch.nn.ZeroPad2d((1, 0, 1, 0)),
+                             torch.nn.Conv2d(8, 3, 4, padding=1), torch.nn.Tanh()),
+         bnn.Sequential(bnn.Upsample(scale_factor=2), bnn.ZeroPad2d((1, 0, 1, 0)), bnn.Conv2d(8, 3, 4, padding=1),
+                        bnn.Tanh()),
+         (2, 8, 9, 9)),
+        (torch.nn.Sequential(torch.nn.ReflectionPad2d(1), torch.nn.Conv2d(32, 32, 3), torch.nn.InstanceNorm2d(32),
+                             torch.nn.ReLU(inplace=True), torch.nn.ReflectionPad2d(1), torch.nn.Conv2d(32, 32, 3),
+                             torch.nn.InstanceNorm2d(32)),
+         bnn.Sequential(bnn.ReflectionPad2d(1), bnn.Conv2d(32, 32, 3), bnn.InstanceNorm2d(32), bnn.ReLU(inplace=True),
+                        bnn.ReflectionPad2d(1), bnn.Conv2d(32, 32, 3), bnn.InstanceNorm2d(32)),
+         (2, 32, 12, 12)),
+    ]:
+        ref, ours = ref.cuda(), ours.cuda()
+        ours.load_state_dict(ref.state_dict())
+        x = torch.randn(*shape, device="cuda")
+        xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        yr, yo = ref(xr), ours(xo)
+        assert yo.shape == yr.shape
+        assert rel_err(yo, yr) < TOL
+        gy = torch.randn_like(yr)
+        yr.backward(gy)
+        yo.backward(gy)
+        assert rel_err(xo.grad, xr.grad) < TOL
+        for (k, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+            if not k.endswith("bias"):  # conv bias in front of a norm: exactly-zero gradient (fp noise only)
+                assert rel_err(po.grad, pr.grad) < TOL, k
+
+
+@pytest.mark.parametrize("eps", [1e-5, 0.8])
+@pytest.mark.parametrize("shape", [(8, 16, 8, 8), (4, 128, 16, 16), (3, 5, 7, 3)])
+def test_batchnorm2d_train(shape, eps):
+    bnn = _mods()
+    torch.manual_seed(5)
+    c = shape[1]
+    ref = torch.nn.BatchNorm2d(c, eps).cuda()
+    ours = bnn.BatchNorm2d(c, eps).cuda()
+    with torch.no_grad():
+        ref.weight.normal_(1, 0.2)
+        ref.bias.normal_(0, 0.2)
+    ours.load_state_dict(ref.state_dict())
+    for _ in range(2):
+        x = torch.randn(*shape, device="cuda") * 2 + 0.5
+        xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        yr, yo = ref(xr), ours(xo)
+        assert rel_err(yo, yr) < 1e-5
+        gy = torch.randn_like(yr)
+        yr.backward(gy)
+        yo.backward(gy)
+        assert rel_err(xo.grad, xr.grad) < 1e-4
+        assert rel_err(ours.weight.grad, ref.weight.grad) < 1e-4
+        assert rel_err(ours.bias.grad, ref.bias.grad) < 1e-4
+        ref.zero_grad()
+        ours.zero_grad()
+    assert rel_err(ours.running_mean, ref.running_mean) < 1e-5
+    assert rel_err(ours.running_var, ref.running_var) < 1e-5   # unbiased variance in the running stat
+    assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+    ref.eval()
+    ours.eval()
+    x = torch.randn(*shape, device="cuda")
+    assert rel_err(ours(x), ref(x)) < 1e-5
+
+
+def test_instancenorm2d():
+    bnn = _mods()
+    torch.manual_seed(6)
+    for shape in [(2, 16, 8, 8), (3, 7, 5, 9), (2, 64, 32, 32)]:
+        ref = torch.nn.InstanceNorm2d(shape[1]).cuda()
+        ours = bnn.InstanceNorm2d(shape[1]).cuda()
+        x = torch.randn(*shape, device="cuda") * 3 - 1
+        xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        yr, yo = ref(xr), ours(xo)
+        assert rel_err(yo, yr) < 1e-5
+        gy = torch.randn_like(yr)
+        yr.backward(gy)
+        yo.backward(gy)
+        assert rel_err(xo.grad, xr.grad) < 1e-4
+    with pytest.raises(ValueError):  # pix2pix down8 has normalize=False because IN on 1x1 raises
+        bnn.InstanceNorm2d(4).cuda()(torch.randn(2, 4, 1, 1, device="cuda"))
+
+
+def test_shape_ops_bit_exact():
+    bnn = _mods()
+    x = torch.randn(3, 6, 7, 5, device="cuda")
+    assert torch.equal(bnn.Upsample(scale_factor=2)(x), torch.nn.Upsample(scale_factor=2)(x))
+    assert torch.equal(bnn.ZeroPad2d((1, 0, 1, 0))(x), torch.nn.ZeroPad2d((1, 0, 1, 0))(x))
+    assert torch.equal(bnn.ReflectionPad2d(3)(x), torch.nn.ReflectionPad2d(3)(x))
+    assert torch.equal(bnn.ReflectionPad2d(1)(x), torch.nn.ReflectionPad2d(1)(x))
+    from b200gan import ops
+    xc = ops.to_cl(x)
+    assert xc.is_contiguous(memory_format=torch.channels_last) and torch.equal(xc, x)
+    back = ops.to_nchw(xc)
+    assert back.is_contiguous() and torch.equal(back, x)
+    # gradients of the index ops: compare with autograd of the stock modules (sums of <= 4 terms)
+    for ours, ref in [(bnn.Upsample(scale_factor=2), torch.nn.Upsample(scale_factor=2)),
+                      (bnn.ReflectionPad2d(2), torch.nn.ReflectionPad2d(2)),
+                      (bnn.ZeroPad2d((1, 0, 1, 0)), torch.nn.ZeroPad2d((1, 0, 1, 0)))]:
+        xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        yo, yr = ours(xo), ref(xr)
+        gy = torch.randn_like(yr)
+        yo.backward(gy)
+        yr.backward(gy)
+        assert rel_err(xo.grad, xr.grad) < 1e-6
+
+
+def test_activations_and_dropout2d_mask_identical():
+    bnn = _mods()
+    x = torch.randn(4, 8, 6, 6, device="cuda")
+    for ours, ref in [(bnn.LeakyReLU(0.2), torch.nn.LeakyReLU(0.2)), (bnn.ReLU(), torch.nn.ReLU()),
+                      (bnn.Tanh(), torch.nn.Tanh()), (bnn.Sigmoid(), torch.nn.Sigmoid())]:
+        xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        yo, yr = ours(xo), ref(xr)
+        assert rel_err(yo, yr) < 1e-6
+        gy = torch.randn_like(yr)
+        yo.backward(gy)
+        yr.backward(gy)
+        assert rel_err(xo.grad, xr.grad) < 1e-5
+    # Dropout2d: same torch RNG call as F.dropout2d -> bit-identical masks under the same seed
+    d_ours, d_ref = bnn.Dropout2d(0.25), torch.nn.Dropout2d(0.25)
+    torch.manual_seed(7)
+    yo = d_ours(x)
+    torch.manual_seed(7)
+    yr = d_ref(x)
+    assert torch.equal(yo == 0, yr == 0)
+    assert rel_err(yo, yr) < 1e-6
+    d_ours.eval()
+    assert d_ours(x) is x
+
+
+def test_conv_linearity_and_adjointness_full_size():
+    """Size-independent properties at the BASELINE sizes (dcgan conv2: [128,128,32,32] after upsample):
+    linearity in x, and <conv(x), dy> == <x, dgrad(dy)> == <w, wgrad(x, dy)>."""
+    bnn = _mods()
+    torch.manual_seed(8)
+    seq = bnn.Sequential(bnn.Upsample(scale_factor=2), bnn.Conv2d(128, 128, 3, 1, 1, bias=False)).cuda()
+    x1 = torch.randn(128, 128, 16, 16, device="cuda", requires_grad=True)
+    x2 = torch.randn(128, 128, 16, 16, device="cuda")
+    y1 = seq(x1)
+    y2 = seq(x2)
+    y12 = seq(x1.detach() + 2 * x2)
+    assert rel_err(y12, y1 + 2 * y2) < TOL
+    dy = torch.randn_like(y1)
+    (dx, dw) = torch.autograd.grad(y1, [x1, seq[1].weight], dy)
+    lhs = (y1.double() * dy.double()).sum().item()
+    assert abs((x1.double() * dx.double()).sum().item() - lhs) < 2e-3 * abs(lhs) + 1.0
+    assert abs((seq[1].weight.double() * dw.double()).sum().item() - lhs) < 2e-3 * abs(lhs) + 1.0
+
+
+def test_empty_batch_and_errors():
+    bnn = _mods()
+    conv = bnn.Conv2d(4, 4, 3, 1, 1).cuda()
+    y = conv(torch.zeros(0, 4, 8, 8, device="cuda"))
+    assert y.shape == (0, 4, 8, 8)
+    with pytest.raises(RuntimeError):
+        conv(torch.zeros(1, 5, 8, 8, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        bnn.Conv2d(4, 4, 3, 1, 1, groups=2).cuda()(torch.zeros(1, 4, 8, 8, device="cuda"))
