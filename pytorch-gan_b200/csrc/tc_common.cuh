@@ -18,8 +18,11 @@ PFN_encodeTiled get_encode_tiled();
 
 // fp32 tensor map, rank <= 5, 128B swizzle, zero fill for out-of-bounds elements.
 // dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
+// atom32: 0 = CU_TENSOR_MAP_SWIZZLE_128B (16-byte swizzle atoms; K-major UMMA operands),
+//         1 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte atoms; the only layout tcgen05 accepts for
+//             MN-major TF32 operands -> UMMA layout type SWIZZLE_128B_BASE32B)
 int make_tmap_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
-                  const uint64_t *strides_bytes, const uint32_t *box);
+                  const uint64_t *strides_bytes, const uint32_t *box, int atom32 = 0);
 
 // ---------------------------------------------------------------------------------------------
 // device: mbarrier
@@ -142,13 +145,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v) {
 // Shared-memory matrix descriptor, 128-byte swizzle:
 //  [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
 //  [46,48) version = 1         [49,52) base offset                [61,64) layout: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//  layout 1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms, 4-row period: MN-major TF32 operands)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                    uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate:

@@ -4,9 +4,10 @@
 // (reference: autograd of nn.Conv2d, dcgan.py:168,182 -> cudnnConvolutionBackwardFilter).
 //
 // As a GEMM the contraction runs over PIXELS, so both operands are "MN-major" in UMMA terms: a TMA
-// box {32 channels, BW, 1, BH, 1} (32 pixels) lands in shared memory as 32 rows x 128 B (128-byte
-// swizzle), i.e. the canonical MN-major SW128 layout ((32 ch contiguous) x (8 pixel rows per atom));
-// one 32-channel chunk per box, chunks LBO bytes apart.  The operand with a multiple of 128 channels is
+// box {32 channels, BW, 1, BH, 1} (32 pixels) lands in shared memory as 32 rows x 128 B.  For TF32 the
+// tensor core accepts MN-major operands only in the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms,
+// 4-row period), which TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; one 32-channel chunk per box,
+// chunks LBO bytes apart, 4-row groups SBO = 512 B apart.  The operand with a multiple of 128 channels is
 // A (M = 128), the other is B (N = 64/128).  Zero padding = TMA out-of-bounds fill on the shifted x box.
 // The upsample-folded convolution (dcgan.py:54-55,58-59) contributes 16 (phase, tap) jobs that read dy
 // through the phase view {2K, Q/2, 2, P/2, N}; a second kernel folds them back into the 3x3 filter.
@@ -132,9 +133,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t sb = sa + A_BYTES;
 #pragma unroll
         for (int k = 0; k < WG_PIX / 8; ++k) {
-          // 8 pixel rows = one swizzle atom (1024 B) per K step; channel chunks are LBO = 4096 B apart
-          uint64_t da = umma_desc_sw128(sa + k * 1024, p.lbo, p.sbo);
-          uint64_t db = umma_desc_sw128(sb + k * 1024, p.lbo, p.sbo);
+          // K step = 8 pixel rows = two 4-row swizzle atoms (SBO = 512 B apart); channel chunks LBO = 4096 B apart
+          uint64_t da = umma_desc_sw128(sa + k * 1024, p.lbo, p.sbo, 1);
+          uint64_t db = umma_desc_sw128(sb + k * 1024, p.lbo, p.sbo, 1);
           umma_tf32(tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty[stage]);
@@ -318,9 +319,9 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   p.x_is_a = pl.x_is_a; p.mtiles = pl.mtiles; p.ntiles = pl.ntiles; p.ldn = pl.ldn; p.mtotal = pl.mtotal;
   p.partial = ws;
   p.lbo = WG_CHUNK_BYTES;
-  p.sbo = 1024;
+  p.sbo = 512;
   if (const char *v = getenv("B200GAN_WG_VARIANT")) {  // bring-up switch for the MN-major descriptor fields
-    if (v[0] == '1') { p.lbo = 1024; p.sbo = WG_CHUNK_BYTES; }
+    if (v[0] == '1') { p.lbo = 512; p.sbo = WG_CHUNK_BYTES; }
   }
 
   CUtensorMap tmX, tmY;
@@ -329,7 +330,7 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
     uint64_t dims[5] = {(uint64_t)g->C, (uint64_t)g->W, 1, (uint64_t)g->H, (uint64_t)g->N};
     uint64_t strides[4] = {(uint64_t)g->C * 4, (uint64_t)g->W * g->C * 4, (uint64_t)g->W * g->C * 4,
                            (uint64_t)g->H * g->W * g->C * 4};
-    if (int e = make_tmap_f32(&tmX, x, 5, dims, strides, box)) return e;
+    if (int e = make_tmap_f32(&tmX, x, 5, dims, strides, box, 1)) return e;
   }
   {
     uint64_t dims[5], strides[4];
@@ -341,7 +342,7 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
       dims[0] = 2 * K; dims[1] = Q / 2; dims[2] = 2; dims[3] = P / 2; dims[4] = g->N;
       strides[0] = 2 * K * 4; strides[1] = Q * K * 4; strides[2] = 2 * Q * K * 4; strides[3] = P * Q * K * 4;
     }
-    if (int e = make_tmap_f32(&tmY, dy, 5, dims, strides, box)) return e;
+    if (int e = make_tmap_f32(&tmY, dy, 5, dims, strides, box, 1)) return e;
   }
   dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
   int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, p, grid, st) : launch_wg<64, 4>(tmX, tmY, p, grid, st);
