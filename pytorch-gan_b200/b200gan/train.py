@@ -2,11 +2,28 @@
 runner used by bench.py.  The step bodies follow the reference loops line by line so that the
 unmodified scripts (via launch.py) and this module execute the same sequence of operator calls.
 """
+import contextlib
+
 import torch
 
 
+@contextlib.contextmanager
+def frozen(module):
+    """Temporarily mark a network's parameters as not requiring grad.  The reference back-propagates the
+    generator loss into the discriminator's weights too (dcgan.py:168) and throws those gradients away at
+    optimizer_D.zero_grad() (dcgan.py:175); skipping that dead weight-gradient work changes no result."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    for p in params:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p in params:
+            p.requires_grad_(True)
+
+
 def dcgan_step(generator, discriminator, opt_g, opt_d, real_imgs, z, loss=None, valid=None, fake=None,
-               reduce_g=None, reduce_d=None):
+               reduce_g=None, reduce_d=None, skip_dead_wgrad=True):
     """implementations/dcgan/dcgan.py:146-183.  `reduce_*`: optional gradient all-reduce hooks invoked
     right before the corresponding optimizer step (data parallel)."""
     loss = loss or torch.nn.BCELoss()
@@ -16,8 +33,9 @@ def dcgan_step(generator, discriminator, opt_g, opt_d, real_imgs, z, loss=None, 
         fake = torch.zeros(n, 1, device=real_imgs.device)   # dcgan.py:148
     opt_g.zero_grad()                                        # :157
     gen_imgs = generator(z)                                  # :163
-    g_loss = loss(discriminator(gen_imgs), valid)            # :166
-    g_loss.backward()                                        # :168
+    with frozen(discriminator) if skip_dead_wgrad else contextlib.nullcontext():
+        g_loss = loss(discriminator(gen_imgs), valid)        # :166
+        g_loss.backward()                                    # :168
     if reduce_g is not None:
         reduce_g()
     opt_g.step()                                             # :169

@@ -311,6 +311,195 @@ conv_wgrad_kernel(GatherP g, const float *__restrict__ xg, const float *__restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Few output channels (K <= 4), C % 4 == 0: L lanes (float4 each) cover the channels of one pixel,
+// 32/L pixel groups per warp, PIX pixels per group in flight (independent loads for latency hiding).
+// Weights sit in shared memory as [k][tap][C] so a lane reads float4 weights next to float4 inputs.
+// HBM-bound: dcgan.py:62 (64->1) reads 134 MB of activations per call.
+// ------------------------------------------------------------------------------------------
+template <int L, int PIX>
+__global__ void __launch_bounds__(256)
+conv_smallk_vec_kernel(GatherP g, EpiP ep, const float *__restrict__ x, const float *__restrict__ wp,
+                       float *__restrict__ y, int K) {
+  extern __shared__ __align__(16) float wsm[];  // [K][R*S][C]
+  const int taps = g.R * g.S;
+  for (int i = threadIdx.x; i < taps * g.C * K; i += blockDim.x) {
+    int k = i % K;
+    int tc = i / K;  // tap * C + c
+    wsm[(size_t)k * taps * g.C + tc] = wp[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sl = lane % L, sg = lane / L;
+  constexpr int GROUPS = 32 / L;
+  const int64_t M = (int64_t)g.N * g.P * g.Q;
+  const int64_t PQ = (int64_t)g.P * g.Q;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t base = warp_global * (GROUPS * PIX); base < M; base += warps_total * (GROUPS * PIX)) {
+    int pn[PIX], pp[PIX], pq[PIX];
+    bool ok[PIX];
+    float acc[PIX][4];
+#pragma unroll
+    for (int i = 0; i < PIX; ++i) {
+      int64_t m = base + sg * PIX + i;
+      ok[i] = m < M;
+      int64_t mm = ok[i] ? m : 0;
+      pq[i] = (int)(mm % g.Q);
+      int64_t t = mm / g.Q;
+      pp[i] = (int)(t % g.P);
+      pn[i] = (int)(t / g.P);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
+    }
+    for (int r = 0; r < g.R; ++r)
+      for (int s = 0; s < g.S; ++s) {
+        int64_t off[PIX];
+#pragma unroll
+        for (int i = 0; i < PIX; ++i) off[i] = ok[i] ? gather_pixel(g, pn[i], pp[i], pq[i], r, s) : -1;
+        const float *wt = wsm + (size_t)(r * g.S + s) * g.C;
+        for (int c0 = sl * 4; c0 < g.C; c0 += L * 4) {
+          float4 xv[PIX];
+#pragma unroll
+          for (int i = 0; i < PIX; ++i)
+            xv[i] = off[i] >= 0 ? __ldg(reinterpret_cast<const float4 *>(x + off[i] + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < K) {
+              float4 w4 = *reinterpret_cast<const float4 *>(wt + (size_t)k * taps * g.C + c0);
+#pragma unroll
+              for (int i = 0; i < PIX; ++i)
+                acc[i][k] += xv[i].x * w4.x + xv[i].y * w4.y + xv[i].z * w4.z + xv[i].w * w4.w;
+            }
+          }
+        }
+      }
+#pragma unroll
+    for (int i = 0; i < PIX; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) acc[i][k] += __shfl_xor_sync(0xffffffffu, acc[i][k], o);
+    if (sl == 0) {
+#pragma unroll
+      for (int i = 0; i < PIX; ++i) {
+        if (!ok[i]) continue;
+        int64_t m = base + sg * PIX + i;
+        int64_t n_img = m / PQ;
+        for (int k = 0; k < K; ++k) {
+          float v = acc[i][k];
+          if (ep.bias) v += __ldg(ep.bias + k);
+          v = apply_act(v, ep.act, ep.slope);
+          if (ep.chan_scale) v *= __ldg(ep.chan_scale + n_img * K + k);
+          if (ep.round_tf32) v = round_tf32(v);
+          y[m * K + k] = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Few gathered channels (C <= 8), K % 4 == 0: one thread per (output pixel, 4 output channels).
+// Output-write bound: DCGAN D block 1 (1->16, dcgan.py:84), the data gradient of the 64->1 output conv
+// (dcgan.py:62), pix2pix/cyclegan first layers (3->64).  Weights [R*S*C][K] live in shared memory.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_smallc_kernel(GatherP g, EpiP ep, const float *__restrict__ x, const float *__restrict__ wp,
+                   float *__restrict__ y, int K) {
+  extern __shared__ __align__(16) float wsm[];  // [R*S*C][K]
+  const int taps = g.R * g.S;
+  for (int i = threadIdx.x; i < taps * g.C * K; i += blockDim.x) wsm[i] = wp[i];
+  __syncthreads();
+  const int KQ = K >> 2;
+  const int64_t M = (int64_t)g.N * g.P * g.Q;
+  const int64_t PQ = (int64_t)g.P * g.Q;
+  const int64_t total = M * KQ;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kq = (int)(idx % KQ);
+    const int64_t m = idx / KQ;
+    const int q = (int)(m % g.Q);
+    const int64_t t = m / g.Q;
+    const int p = (int)(t % g.P);
+    const int n = (int)(t / g.P);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < g.R; ++r)
+      for (int s = 0; s < g.S; ++s) {
+        int64_t off = gather_pixel(g, n, p, q, r, s);
+        if (off < 0) continue;
+        const float *wt = wsm + (size_t)((r * g.S + s) * g.C) * K + kq * 4;
+        for (int c = 0; c < g.C; ++c) {
+          float xv = __ldg(x + off + c);
+          float4 w4 = *reinterpret_cast<const float4 *>(wt + (size_t)c * K);
+          acc.x = fmaf(xv, w4.x, acc.x);
+          acc.y = fmaf(xv, w4.y, acc.y);
+          acc.z = fmaf(xv, w4.z, acc.z);
+          acc.w = fmaf(xv, w4.w, acc.w);
+        }
+      }
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    const int64_t n_img = m / PQ;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = kq * 4 + j;
+      if (ep.bias) v[j] += __ldg(ep.bias + k);
+      v[j] = apply_act(v[j], ep.act, ep.slope);
+      if (ep.chan_scale) v[j] *= __ldg(ep.chan_scale + n_img * K + k);
+      if (ep.round_tf32) v[j] = round_tf32(v[j]);
+    }
+    *reinterpret_cast<float4 *>(y + m * K + kq * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient with few dense channels (Cd <= 4): thread per (r,s,cg) column, loop over a pixel range,
+// block-wide partial sums -> atomicAdd.  dcgan.py:62 (64->1): a 524288-pixel reduction reading 134 MB.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_wgrad_smallcd_kernel(GatherP g, const float *__restrict__ xg, const float *__restrict__ dn,
+                          float *__restrict__ dw, int Cd, int64_t m_per_block) {
+  const int Ktot = g.R * g.S * g.C;
+  const int kd = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool kok = kd < Ktot;
+  int c = 0, r = 0, s = 0;
+  if (kok) {
+    c = kd % g.C;
+    int t = kd / g.C;
+    s = t % g.S;
+    r = t / g.S;
+  }
+  const int64_t M = (int64_t)g.N * g.P * g.Q;
+  const int64_t m0 = (int64_t)blockIdx.x * m_per_block;
+  int64_t m1 = m0 + m_per_block;
+  if (m1 > M) m1 = M;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (kok) {
+    int q = (int)(m0 % g.Q);
+    int64_t t = m0 / g.Q;
+    int p = (int)(t % g.P);
+    int n = (int)(t / g.P);
+    for (int64_t m = m0; m < m1; ++m) {
+      int64_t off = gather_pixel(g, n, p, q, r, s);
+      if (off >= 0) {
+        float xv = __ldg(xg + off + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < Cd) acc[j] = fmaf(xv, __ldg(dn + m * Cd + j), acc[j]);
+      }
+      if (++q == g.Q) {
+        q = 0;
+        if (++p == g.P) {
+          p = 0;
+          ++n;
+        }
+      }
+    }
+    for (int j = 0; j < Cd; ++j) atomicAdd(dw + (((int64_t)j * g.C + c) * g.R + r) * g.S + s, acc[j]);
+  }
+}
+
 // column sums: out[c] += sum_m x[m][c]   (bias gradient). out zeroed by caller.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t M, int C,
@@ -361,10 +550,35 @@ int simt_gather_gemm(int N, int H, int W, int C, int P, int Q, int K, int R, int
   if (M == 0 || K == 0) return B200GAN_OK;
   int Ktot = R * S * C;
   size_t wbytes = (size_t)Ktot * K * sizeof(float);
-  if (K <= 4 && C >= 32 && wbytes <= 48 * 1024) {
+  const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+  if (K <= 4 && C % 4 == 0 && C >= 16 && wbytes <= 48 * 1024 && aligned) {
+    // few output channels: lanes over channels (float4), several pixels in flight per lane group
+    const int64_t blocks_max = 148 * 8;
+    if (C >= 128) {
+      int64_t blocks = ceil_div64(M, 8 * 1 * 4);
+      if (blocks > blocks_max) blocks = blocks_max;
+      conv_smallk_vec_kernel<32, 4><<<(unsigned)blocks, 256, wbytes, st>>>(g, e, x, wp, y, K);
+    } else if (C >= 64) {
+      int64_t blocks = ceil_div64(M, 8 * 2 * 4);
+      if (blocks > blocks_max) blocks = blocks_max;
+      conv_smallk_vec_kernel<16, 4><<<(unsigned)blocks, 256, wbytes, st>>>(g, e, x, wp, y, K);
+    } else if (C >= 32) {
+      int64_t blocks = ceil_div64(M, 8 * 4 * 4);
+      if (blocks > blocks_max) blocks = blocks_max;
+      conv_smallk_vec_kernel<8, 4><<<(unsigned)blocks, 256, wbytes, st>>>(g, e, x, wp, y, K);
+    } else {
+      int64_t blocks = ceil_div64(M, 8 * 8 * 4);
+      if (blocks > blocks_max) blocks = blocks_max;
+      conv_smallk_vec_kernel<4, 4><<<(unsigned)blocks, 256, wbytes, st>>>(g, e, x, wp, y, K);
+    }
+  } else if (K <= 4 && C >= 32 && wbytes <= 48 * 1024) {
     int64_t blocks = ceil_div64(M, 8);
     if (blocks > 148 * 64) blocks = 148 * 64;
     conv_gather_smallk_kernel<4><<<(unsigned)blocks, 256, wbytes, st>>>(g, e, x, wp, y, K);
+  } else if (C <= 8 && K % 4 == 0 && K >= 8 && wbytes <= 48 * 1024 && aligned) {
+    int64_t blocks = ceil_div64(M * (K / 4), 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    conv_smallc_kernel<<<(unsigned)blocks, 256, wbytes, st>>>(g, e, x, wp, y, K);
   } else {
     dim3 grid((unsigned)ceil_div64(M, FBM), (unsigned)ceil_div(K, FBN));
     conv_gather_gemm_kernel<<<grid, 256, 0, st>>>(g, e, x, wp, y, K);
@@ -382,6 +596,17 @@ int simt_wgrad(int N, int H, int W, int Cg, int P, int Q, int Cd, int R, int S, 
   int Ktot = R * S * Cg;
   B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)Ktot * Cd * sizeof(float), st));
   if (M == 0) return B200GAN_OK;
+  if (Cd <= 4) {
+    int yb = ceil_div(Ktot, 256);
+    int64_t xb = (148 * 8) / yb;
+    if (xb < 1) xb = 1;
+    int64_t m_per_block = ceil_div64(M, xb);
+    if (m_per_block < 64) m_per_block = 64;
+    xb = ceil_div64(M, m_per_block);
+    conv_wgrad_smallcd_kernel<<<dim3((unsigned)xb, (unsigned)yb), 256, 0, st>>>(g, xg, dn, dw, Cd, m_per_block);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   int tiles = ceil_div(Ktot, FBM) * ceil_div(Cd, FBN);
   int64_t splits = (148 * 4 + tiles - 1) / tiles;
   int64_t max_splits = ceil_div64(M, 128);
