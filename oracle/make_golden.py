@@ -163,7 +163,51 @@ def golden_ops(seed=0):
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def golden_wgan_gp(img_size=32, batch=64, seed=0):
+    """wgan_gp.py: the reference's own compute_gradient_penalty (+ the double backward) on seeded inputs."""
+    ref = run_reference_script("wgan_gp/wgan_gp.py", ["--n_epochs", "0", "--img_size", str(img_size), "--batch_size",
+                                                      str(batch)], seed)
+    g_ref, d_ref, cgp = ref["generator"], ref["discriminator"], ref["compute_gradient_penalty"]
+    g_or, d_or = ref_models.build_wgan_gp(img_size, seed=seed)
+    _assert_same_state(g_ref, g_or, "wgan_gp G")
+    _assert_same_state(d_ref, d_or, "wgan_gp D")
+    real = ref_models.synthetic_images(batch, 1, img_size, img_size, seed=seed)
+    z = ref_models.synthetic_z(batch, seed=seed)
+    g_ref.train()
+    with torch.no_grad():
+        fake = g_ref(z)
+    lam = ref["lambda_gp"]
+    np.random.seed(seed + 5)
+    d_ref.zero_grad()
+    gp_ref = cgp(d_ref, real, fake)           # draws alpha from numpy inside (wgan_gp.py:122)
+    (lam * gp_ref).backward()
+    alpha = ref_models.synthetic_alpha(batch, seed=seed + 5)
+    d_or.zero_grad()
+    gp_or = ref_models.compute_gradient_penalty(d_or, real, fake, alpha)
+    (lam * gp_or).backward()
+    assert torch.equal(gp_ref, gp_or), "wgan_gp gradient penalty: oracle != reference"
+    for (k, pr), (_, po) in zip(d_ref.named_parameters(), d_or.named_parameters()):
+        if pr.grad is None:
+            assert po.grad is None or float(po.grad.abs().max()) == 0.0, k
+        else:
+            assert torch.equal(pr.grad, po.grad), f"wgan_gp D grad {k}"
+    grads = {k: (None if p.grad is None else p.grad.clone()) for k, p in d_ref.named_parameters()}
+    fix = dict(img_size=img_size, batch=batch, seed=seed, real=real, fake=fake, alpha=alpha, lambda_gp=lam,
+               gp=gp_ref.detach(),
+               dW1_head=grads["model.0.weight"][:4].clone(), dW1_norm=grads["model.0.weight"].double().norm().item(),
+               dW2_head=grads["model.2.weight"][:8].clone(), dW2_norm=grads["model.2.weight"].double().norm().item(),
+               dW3=grads["model.4.weight"].clone(),
+               bias_grads_zero=all(grads[k] is None or float(grads[k].abs().max()) == 0.0
+                                   for k in ("model.0.bias", "model.2.bias", "model.4.bias")),
+               torch_version=torch.__version__, reference="wgan_gp/wgan_gp.py@36d3c77")
+    path = os.path.join(GOLD, f"wgan_gp_{img_size}_b{batch}.pt")
+    torch.save(fix, path)
+    print(f"wgan_gp img {img_size} batch {batch}: oracle == reference (bit-exact), gp = {gp_ref.item():.6f}; "
+          f"bias grads zero: {fix['bias_grads_zero']}; wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     golden_dcgan(32, 8)
     golden_ops()
+    golden_wgan_gp()

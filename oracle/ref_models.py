@@ -112,3 +112,61 @@ def synthetic_z(n, latent_dim=100, seed=0):
     # dcgan.py:160 draws z with numpy
     rng = np.random.RandomState(seed)
     return torch.tensor(rng.normal(0, 1, (n, latent_dim)), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# WGAN-GP (BASELINE config 2)
+# ------------------------------------------------------------------------------------------------
+class WGANGPGenerator(nn.Module):
+    # wgan_gp/wgan_gp.py:42-65
+    def __init__(self, img_shape=(1, 32, 32), latent_dim=100):
+        super().__init__()
+        self.img_shape = tuple(img_shape)
+
+        def block(i, o, normalize=True):
+            layers = [nn.Linear(i, o)]
+            if normalize:
+                layers.append(nn.BatchNorm1d(o, 0.8))
+            layers.append(nn.LeakyReLU(0.2, inplace=True))
+            return layers
+
+        self.model = nn.Sequential(*block(latent_dim, 128, normalize=False), *block(128, 256), *block(256, 512),
+                                   *block(512, 1024), nn.Linear(1024, int(np.prod(img_shape))), nn.Tanh())
+
+    def forward(self, z):
+        img = self.model(z)
+        return img.view(img.shape[0], *self.img_shape)
+
+
+class WGANGPDiscriminator(nn.Module):
+    # wgan_gp/wgan_gp.py:68-83
+    def __init__(self, img_shape=(1, 32, 32)):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(int(np.prod(img_shape)), 512), nn.LeakyReLU(0.2, inplace=True),
+                                   nn.Linear(512, 256), nn.LeakyReLU(0.2, inplace=True), nn.Linear(256, 1))
+
+    def forward(self, img):
+        return self.model(img.view(img.shape[0], -1))
+
+
+def build_wgan_gp(img_size=32, channels=1, latent_dim=100, seed=0):
+    """wgan_gp.py:90-91: G then D, default torch init (no weights_init_normal in this script)."""
+    torch.manual_seed(seed)
+    shape = (channels, img_size, img_size)
+    return WGANGPGenerator(shape, latent_dim), WGANGPDiscriminator(shape)
+
+
+def compute_gradient_penalty(D, real_samples, fake_samples, alpha):
+    """wgan_gp.py:119-138 with the numpy draw of alpha (:122) passed in."""
+    interpolates = (alpha * real_samples + ((1 - alpha) * fake_samples)).requires_grad_(True)
+    d_interpolates = D(interpolates)
+    fake = torch.ones(real_samples.shape[0], 1, device=real_samples.device)
+    gradients = torch.autograd.grad(outputs=d_interpolates, inputs=interpolates, grad_outputs=fake,
+                                    create_graph=True, retain_graph=True, only_inputs=True)[0]
+    gradients = gradients.view(gradients.size(0), -1)
+    return ((gradients.norm(2, dim=1) - 1) ** 2).mean()
+
+
+def synthetic_alpha(n, seed=0):
+    rng = np.random.RandomState(seed)
+    return torch.tensor(rng.random_sample((n, 1, 1, 1)), dtype=torch.float32)

@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ALGO_SIMT, ALGO_TC, PAD_REFLECT, PAD_ZERO, ConvGeom, Epilogue, NormDesc)
+from ._lib import (ACT_NONE, ALGO_SIMT, ALGO_TC, PAD_REFLECT, PAD_ZERO, ConvGeom, Epilogue, GpMlpDesc, NormDesc)
 
 CL = torch.channels_last
 
@@ -259,3 +259,24 @@ def act_forward(x, act, slope, mask=None, mask_per_channel=False):
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, grad_scale, step):
     _lib.check(_lib.load().b200gan_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
                                              beta1, beta2, eps, grad_scale, step.data_ptr(), _stream()), "adam_step")
+
+
+def gp_mlp_fwd_bwd(xi, w1, b1, w2, b2, w3, slope, lambda_gp):
+    """Gradient penalty of the 3-layer MLP critic and its weight gradients in one kernel
+    (wgan_gp.py:119-138 + the double backward at wgan_gp.py:173).  Returns (gp, dW1, dW2, dW3)."""
+    for t_ in (xi, w1, b1, w2, b2, w3):
+        _require_cuda(t_, "gp_mlp operand")
+    lib = _lib.load()
+    xi = xi.contiguous().view(xi.shape[0], -1)
+    d = GpMlpDesc()
+    d.N, d.Din, d.H1, d.H2 = xi.shape[0], xi.shape[1], w1.shape[0], w2.shape[0]
+    d.slope, d.lambda_gp = slope, lambda_gp
+    if w1.shape[1] != d.Din or w2.shape[1] != d.H1 or w3.numel() != d.H2:
+        raise RuntimeError("b200gan gp_mlp: layer shapes do not chain")
+    ws = torch.empty(lib.b200gan_gp_mlp_workspace_floats(ctypes.byref(d)), device=xi.device, dtype=torch.float32)
+    gp = torch.empty((), device=xi.device, dtype=torch.float32)
+    dw1, dw2, dw3 = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(w3)
+    _lib.check(lib.b200gan_gp_mlp_fwd_bwd(ctypes.byref(d), xi.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                          b2.data_ptr(), w3.data_ptr(), gp.data_ptr(), dw1.data_ptr(), dw2.data_ptr(),
+                                          dw3.data_ptr(), ws.data_ptr(), _stream()), "gp_mlp_fwd_bwd")
+    return gp, dw1, dw2, dw3

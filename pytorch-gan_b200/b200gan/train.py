@@ -50,6 +50,44 @@ def dcgan_step(generator, discriminator, opt_g, opt_d, real_imgs, z, loss=None, 
     return g_loss.detach(), d_loss.detach(), gen_imgs.detach()
 
 
+def wgan_gp_critic_step(generator, discriminator, opt_d, real_imgs, z, alpha, lambda_gp=10.0, fused_gp=True):
+    """One critic iteration of implementations/wgan_gp/wgan_gp.py:155-174.  `alpha` [N,1,1,1] is the
+    interpolation weight the reference draws with numpy (wgan_gp.py:122).  With fused_gp the penalty and its
+    double backward run in the single gp_mlp kernel; otherwise through autograd exactly like the reference.
+    The reference leaves fake_imgs attached (dead back-prop into G, whose grads are zeroed at :176); here the
+    fakes are detached -- identical D update."""
+    from . import functional as F
+    opt_d.zero_grad()                                                     # :155
+    with torch.no_grad():
+        fake_imgs = generator(z)                                          # :161
+    real_validity = discriminator(real_imgs)                              # :164
+    fake_validity = discriminator(fake_imgs)                              # :166
+    interpolates = alpha * real_imgs + (1 - alpha) * fake_imgs            # :124
+    if fused_gp:
+        gp_term = F.gradient_penalty_mlp(discriminator.model, interpolates, lambda_gp)
+    else:
+        interpolates = interpolates.requires_grad_(True)
+        d_int = discriminator(interpolates)                               # :125
+        grads = torch.autograd.grad(outputs=d_int, inputs=interpolates, grad_outputs=torch.ones_like(d_int),
+                                    create_graph=True, retain_graph=True, only_inputs=True)[0]   # :128-135
+        grads = grads.view(grads.size(0), -1)
+        gp_term = lambda_gp * ((grads.norm(2, dim=1) - 1) ** 2).mean()    # :137
+    d_loss = -torch.mean(real_validity) + torch.mean(fake_validity) + gp_term   # :171
+    d_loss.backward()                                                     # :173
+    opt_d.step()                                                          # :174
+    return d_loss.detach(), gp_term.detach()
+
+
+def wgan_gp_generator_step(generator, discriminator, opt_g, z):
+    """wgan_gp.py:176-193."""
+    opt_g.zero_grad()
+    with frozen(discriminator):
+        g_loss = -torch.mean(discriminator(generator(z)))
+        g_loss.backward()
+    opt_g.step()
+    return g_loss.detach()
+
+
 class GraphedStep:
     """Capture one training step into a CUDA graph (static input/output buffers) and replay it.
     The step function must be free of host synchronisation; optimizers must be `capturable`."""

@@ -82,3 +82,45 @@ class DCGANDiscriminator(tnn.Module):
         out = self.model(img)
         out = out.view(out.shape[0], -1)
         return self.adv_layer(out)
+
+
+class WGANGPGenerator(tnn.Module):
+    """wgan_gp/wgan_gp.py:42-65 (MLP; BatchNorm1d(out, 0.8): second positional argument is eps)."""
+
+    def __init__(self, img_shape=(1, 32, 32), latent_dim=100, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        self.img_shape = tuple(img_shape)
+
+        def block(i, o, normalize=True):
+            layers = [nn.Linear(i, o)]
+            if normalize:
+                layers.append(nn.BatchNorm1d(o, 0.8))
+            layers.append(nn.LeakyReLU(0.2, inplace=True))
+            return layers
+
+        n_out = 1
+        for v in self.img_shape:
+            n_out *= v
+        self.model = nn.Sequential(*block(latent_dim, 128, normalize=False), *block(128, 256), *block(256, 512),
+                                   *block(512, 1024), nn.Linear(1024, n_out), nn.Tanh())
+
+    def forward(self, z):
+        img = self.model(z)
+        return img.view(img.shape[0], *self.img_shape)
+
+
+class WGANGPDiscriminator(tnn.Module):
+    """wgan_gp/wgan_gp.py:68-83."""
+
+    def __init__(self, img_shape=(1, 32, 32), nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        n_in = 1
+        for v in img_shape:
+            n_in *= v
+        self.model = nn.Sequential(nn.Linear(n_in, 512), nn.LeakyReLU(0.2, inplace=True), nn.Linear(512, 256),
+                                   nn.LeakyReLU(0.2, inplace=True), nn.Linear(256, 1))
+
+    def forward(self, img):
+        return self.model(img.view(img.shape[0], -1))

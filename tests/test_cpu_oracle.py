@@ -176,3 +176,57 @@ def test_mlp_modules_run_stock_on_cpu():
                          bnn.Sigmoid())
     y = net(torch.randn(4, 10))
     assert y.shape == (4, 1) and bool((y > 0).all())
+
+
+def test_wgan_gp_oracle_and_closed_form_against_reference_golden(golden_dir):
+    """The golden file holds the reference's own compute_gradient_penalty output and the D gradients of
+    lambda*gp (oracle/make_golden.py).  Check (a) the torch restatement, (b) the closed form the CUDA kernel
+    implements (numpy float64)."""
+    fix = torch.load(os.path.join(golden_dir, "wgan_gp_32_b64.pt"), weights_only=False)
+    _, d = ref_models.build_wgan_gp(fix["img_size"], seed=fix["seed"])
+    gp = ref_models.compute_gradient_penalty(d, fix["real"], fix["fake"], fix["alpha"])
+    assert abs(gp.item() - fix["gp"].item()) < 1e-6
+    (fix["lambda_gp"] * gp).backward()
+    assert rel_err(d.model[4].weight.grad, fix["dW3"]) < 1e-5
+    assert fix["bias_grads_zero"]
+    xi = (fix["alpha"] * fix["real"] + (1 - fix["alpha"]) * fix["fake"]).double().numpy()
+    w = [p.detach().double().numpy() for p in d.parameters()]
+    gp_c, dw1, dw2, dw3 = np_ops.gp_mlp_closed_form(xi, w[0], w[1], w[2], w[3], w[4], 0.2, fix["lambda_gp"])
+    assert abs(gp_c - fix["lambda_gp"] * fix["gp"].item()) < 1e-5 * abs(gp_c)
+    assert rel_err(torch.from_numpy(dw3.reshape(1, -1)), fix["dW3"]) < 1e-5
+    assert rel_err(torch.from_numpy(dw1[:4]), fix["dW1_head"]) < 1e-5
+    assert rel_err(torch.from_numpy(dw2[:8]), fix["dW2_head"]) < 1e-5
+    assert abs(np.linalg.norm(dw1) - fix["dW1_norm"]) < 1e-5 * fix["dW1_norm"]
+    assert abs(np.linalg.norm(dw2) - fix["dW2_norm"]) < 1e-5 * fix["dW2_norm"]
+
+
+REF = "/root/reference/implementations"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present on this box")
+def test_launcher_runs_unmodified_gan_script_on_cpu_config0():
+    """BASELINE config 0: implementations/gan/gan.py, 28x28 synthetic, batch 64, CPU -- the unmodified script
+    under the launcher with the drop-in classes patched in (MLP: stock ops through the same classes) prints the
+    same losses as the stock run."""
+    from b200gan import launch
+    args = ["--n_epochs", "1", "--batch_size", "64", "--sample_interval", "1000"]
+    ours = launch.run(os.path.join(REF, "gan", "gan.py"), args, iters=3, seed=0, stock=False, quiet=True)
+    stock = launch.run(os.path.join(REF, "gan", "gan.py"), args, iters=3, seed=0, stock=True, quiet=True)
+    lines = [l for l in ours["__b200_stdout__"].splitlines() if "[D loss" in l]
+    assert len(lines) == 3
+    assert ours["__b200_stdout__"] == stock["__b200_stdout__"]
+    assert type(ours["generator"].model[1]).__name__ == "LeakyReLU"
+    from b200gan import nn as bnn
+    assert isinstance(ours["generator"].model, bnn.Sequential)
+    assert not isinstance(stock["generator"].model, bnn.Sequential)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present on this box")
+def test_launcher_builds_dcgan_with_drop_in_modules():
+    from b200gan import launch, nn as bnn
+    g = launch.run(os.path.join(REF, "dcgan", "dcgan.py"), ["--n_epochs", "0", "--img_size", "32"], iters=1, seed=0,
+                   quiet=True)
+    gen, ref = g["generator"], ref_models.build_dcgan(32, seed=0)[0]
+    assert isinstance(gen.conv_blocks, bnn.Sequential) and isinstance(gen.conv_blocks[2], bnn.Conv2d)
+    for k, v in ref.state_dict().items():   # same init draws as the stock run of the same script
+        assert torch.equal(gen.state_dict()[k], v), k
