@@ -45,24 +45,21 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int validate_geom(const b200gan_conv_geom *g);
 
 // ---- device helpers ---------------------------------------------------------------------
+// if-chains, not `switch`: a switch in an unrolled loop is lowered to one indirect branch (BRX) per element
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
-  switch (act) {
-    case B200GAN_ACT_LRELU: return v > 0.f ? v : v * slope;
-    case B200GAN_ACT_RELU: return v > 0.f ? v : 0.f;
-    case B200GAN_ACT_TANH: return tanhf(v);
-    case B200GAN_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    default: return v;
-  }
+  if (act == B200GAN_ACT_NONE) return v;
+  if (act == B200GAN_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == B200GAN_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == B200GAN_ACT_TANH) return tanhf(v);
+  return 1.f / (1.f + expf(-v));
 }
 // derivative of the activation expressed through its OUTPUT y
 __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
-  switch (act) {
-    case B200GAN_ACT_LRELU: return y > 0.f ? 1.f : slope;
-    case B200GAN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case B200GAN_ACT_TANH: return 1.f - y * y;
-    case B200GAN_ACT_SIGMOID: return y * (1.f - y);
-    default: return 1.f;
-  }
+  if (act == B200GAN_ACT_NONE) return 1.f;
+  if (act == B200GAN_ACT_LRELU) return y > 0.f ? 1.f : slope;
+  if (act == B200GAN_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == B200GAN_ACT_TANH) return 1.f - y * y;
+  return y * (1.f - y);
 }
 // round-to-nearest fp32 -> tf32 (10-bit mantissa), result kept in an fp32 container
 __device__ __forceinline__ float round_tf32(float v) {

@@ -21,6 +21,8 @@ struct GatherP {
   int pad_mode, up;    // only for mode 0
   int Hv, Wv;          // H*up, W*up
   int mode;            // 0: ih = p*stride - pad + r ; 1: ih = (p + pad - r)/stride (if divisible)
+  int cls;             // mode 1, stride > 1: blockIdx.z enumerates the stride^2 output parity classes, each with
+                       // its own compact tap set (no work on taps that can never divide); 1 = off
 };
 
 // returns element offset of pixel (n, ih, iw) in the stored tensor or -1 if it contributes 0
@@ -73,10 +75,24 @@ conv_gather_gemm_kernel(GatherP g, EpiP ep, const float *__restrict__ x,
   __shared__ __align__(16) float Bs[FBK][FBN + FPAD];
   const int tid = threadIdx.x;
   const int tm = tid >> 4, tn = tid & 15;
-  const int64_t M = (int64_t)g.N * g.P * g.Q;
-  const int Ktot = g.R * g.S * g.C;
+  // parity-class decomposition of the transposed gather (stride-2 dgrad: 9 taps -> 1/2/2/4 per class)
+  const int cls = g.cls;
+  int pa = 0, pb = 0, r0 = 0, s0 = 0, Rc = g.R, Sc = g.S, Pc = g.P, Qc = g.Q;
+  if (cls > 1) {
+    pa = blockIdx.z / cls;
+    pb = blockIdx.z % cls;
+    r0 = (pa + g.pad_t) % cls;
+    s0 = (pb + g.pad_l) % cls;
+    Rc = r0 < g.R ? (g.R - r0 + cls - 1) / cls : 0;
+    Sc = s0 < g.S ? (g.S - s0 + cls - 1) / cls : 0;
+    Pc = pa < g.P ? (g.P - pa + cls - 1) / cls : 0;
+    Qc = pb < g.Q ? (g.Q - pb + cls - 1) / cls : 0;
+  }
+  const int64_t M = (int64_t)g.N * Pc * Qc;
+  const int Ktot = Rc * Sc * g.C;
   const int64_t m0 = (int64_t)blockIdx.x * FBM;
   const int n0 = blockIdx.y * FBN;
+  if (m0 >= M) return;
 
   // the 4 A rows this thread gathers: rows (tid>>4) + 16*i, column kk = tid & 15
   const int a_kk = tid & 15;
@@ -87,10 +103,10 @@ conv_gather_gemm_kernel(GatherP g, EpiP ep, const float *__restrict__ x,
     int64_t m = m0 + (tid >> 4) + 16 * i;
     a_ok[i] = m < M;
     int64_t mm = a_ok[i] ? m : 0;
-    a_q[i] = (int)(mm % g.Q);
-    int64_t t = mm / g.Q;
-    a_p[i] = (int)(t % g.P);
-    a_n[i] = (int)(t / g.P);
+    a_q[i] = pb + cls * (int)(mm % Qc);
+    int64_t t = mm / Qc;
+    a_p[i] = pa + cls * (int)(t % Pc);
+    a_n[i] = (int)(t / Pc);
   }
   const int b_n = tid & 63, b_k = tid >> 6;
 
@@ -108,8 +124,8 @@ conv_gather_gemm_kernel(GatherP g, EpiP ep, const float *__restrict__ x,
       if (kok) {
         c = k % g.C;
         int t = k / g.C;
-        s = t % g.S;
-        r = t / g.S;
+        s = s0 + cls * (t % Sc);
+        r = r0 + cls * (t / Sc);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -126,7 +142,12 @@ conv_gather_gemm_kernel(GatherP g, EpiP ep, const float *__restrict__ x,
       int k = k0 + b_k + 4 * i;
       int n = n0 + b_n;
       float v = 0.f;
-      if (k < Ktot && n < K) v = __ldg(wp + (int64_t)k * K + n);
+      if (k < Ktot && n < K) {
+        int c = k % g.C;
+        int t = k / g.C;
+        int s = s0 + cls * (t % Sc), r = r0 + cls * (t / Sc);
+        v = __ldg(wp + ((int64_t)(r * g.S + s) * g.C + c) * K + n);
+      }
       Bs[b_k + 4 * i][b_n] = v;
     }
     __syncthreads();
@@ -144,12 +165,15 @@ conv_gather_gemm_kernel(GatherP g, EpiP ep, const float *__restrict__ x,
     __syncthreads();
   }
 
-  const int64_t PQ = (int64_t)g.P * g.Q;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int64_t m = m0 + tm * 4 + i;
     if (m >= M) continue;
-    int64_t n_img = m / PQ;
+    const int q = pb + cls * (int)(m % Qc);
+    const int64_t t = m / Qc;
+    const int pp = pa + cls * (int)(t % Pc);
+    const int64_t n_img = t / Pc;
+    const int64_t mfull = (n_img * g.P + pp) * g.Q + q;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = n0 + tn * 4 + j;
@@ -159,7 +183,7 @@ conv_gather_gemm_kernel(GatherP g, EpiP ep, const float *__restrict__ x,
       v = apply_act(v, ep.act, ep.slope);
       if (ep.chan_scale) v *= __ldg(ep.chan_scale + n_img * K + k);
       if (ep.round_tf32) v = round_tf32(v);
-      y[m * K + k] = v;
+      y[mfull * K + k] = v;
     }
   }
 }
@@ -500,6 +524,213 @@ conv_wgrad_smallcd_kernel(GatherP g, const float *__restrict__ xg, const float *
   }
 }
 
+
+// ==========================================================================================
+// Lean kernels for the HBM-bound 3x3 / stride-1 / zero-pad layers with one tiny channel side
+// (dcgan.py:62: Conv2d(64, 1, 3, 1, 1) on [128,64,64,64] -- 134 MB of activations per pass).
+// No generic gather: rows/cols are walked incrementally, every input element is loaded once per
+// pixel group and reused from registers across the taps.
+// ==========================================================================================
+
+// fprop, K <= 4 output channels: L lanes x float4 cover the C channels of a pixel; each lane group
+// produces PX = 4 consecutive output pixels of one row from a (3 x 6) window of input pixels.
+template <int L, int KK>
+__global__ void __launch_bounds__(256)
+conv3x3s1_smallk_kernel(const float *__restrict__ x, const float *__restrict__ wp, float *__restrict__ y, EpiP ep,
+                        int N, int H, int W, int C, int dir) {
+  // wp: [3][3][C][KK] (SIMT fprop pack).  dir = +1: y[p] = sum x[p + r - 1] w[r] (conv fprop, pad 1);
+  // dir = -1: taps mirrored (transposed gather: y[p] = sum x[p + 1 - r] w[r]).
+  extern __shared__ __align__(16) float wsm[];  // [KK][9][C]
+  for (int i = threadIdx.x; i < 9 * C * KK; i += blockDim.x) {
+    int k = i % KK, tc = i / KK;
+    wsm[(size_t)k * 9 * C + tc] = wp[i];
+  }
+  __syncthreads();
+  constexpr int PX = 4, GROUPS = 32 / L;
+  const int lane = threadIdx.x & 31, sl = lane % L, sg = lane / L;
+  const int QG = (W + PX - 1) / PX;
+  const int64_t ngroups = (int64_t)N * H * QG;
+  const int64_t gstride = (int64_t)gridDim.x * (blockDim.x >> 5) * GROUPS;
+  for (int64_t gi = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + sg;
+       gi - sg < ngroups; gi += gstride) {  // whole warp iterates together (shuffles below)
+    const bool gok = gi < ngroups;
+    const int64_t g2 = gok ? gi : 0;
+    const int q0 = (int)(g2 % QG) * PX;
+    const int64_t t = g2 / QG;
+    const int p = (int)(t % H), n = (int)(t / H);
+    float acc[PX][KK];
+#pragma unroll
+    for (int o = 0; o < PX; ++o)
+#pragma unroll
+      for (int k = 0; k < KK; ++k) acc[o][k] = 0.f;
+    for (int c0 = sl * 4; c0 < C; c0 += L * 4) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int ih = p + dir * (r - 1);
+        if (!gok || ih < 0 || ih >= H) continue;
+        const float *xrow = x + ((int64_t)(n * H + ih) * W) * C + c0;
+        float4 xv[PX + 2];
+#pragma unroll
+        for (int j = 0; j < PX + 2; ++j) {
+          const int iw = q0 + j - 1;
+          xv[j] = (iw >= 0 && iw < W) ? __ldg(reinterpret_cast<const float4 *>(xrow + (int64_t)iw * C))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+          // input column offset sx-1 relative to the output pixel  <->  filter column s = 1 + dir*(sx-1)
+          const int s = 1 + dir * (sx - 1);
+#pragma unroll
+          for (int k = 0; k < KK; ++k) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(wsm + (size_t)k * 9 * C + (size_t)(r * 3 + s) * C + c0);
+#pragma unroll
+            for (int o = 0; o < PX; ++o) {
+              const float4 v = xv[o + sx];
+              acc[o][k] += v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < PX; ++o)
+#pragma unroll
+      for (int k = 0; k < KK; ++k)
+#pragma unroll
+        for (int d = L / 2; d > 0; d >>= 1) acc[o][k] += __shfl_xor_sync(0xffffffffu, acc[o][k], d);
+    if (gok && sl == 0) {
+#pragma unroll
+      for (int o = 0; o < PX; ++o) {
+        if (q0 + o >= W) continue;
+        const int64_t m = ((int64_t)(n * H + p) * W) + q0 + o;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+          float v = acc[o][k];
+          if (ep.bias) v += __ldg(ep.bias + k);
+          v = apply_act(v, ep.act, ep.slope);
+          if (ep.chan_scale) v *= __ldg(ep.chan_scale + (int64_t)n * KK + k);
+          if (ep.round_tf32) v = round_tf32(v);
+          y[m * KK + k] = v;
+        }
+      }
+    }
+  }
+}
+
+// few gathered channels (CG <= 4), many outputs (K % 8 == 0): thread = (pixel, 8 output channels).
+template <int CG>
+__global__ void __launch_bounds__(256)
+conv3x3s1_smallc_kernel(const float *__restrict__ x, const float *__restrict__ wp, float *__restrict__ y, EpiP ep,
+                        int N, int H, int W, int K, int dir) {
+  extern __shared__ __align__(16) float wsm[];  // [9][CG][K]
+  for (int i = threadIdx.x; i < 9 * CG * K; i += blockDim.x) wsm[i] = wp[i];
+  __syncthreads();
+  const int KO = K >> 3;
+  const int64_t total = (int64_t)N * H * W * KO;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ko = (int)(idx % KO);
+    const int64_t m = idx / KO;
+    const int q = (int)(m % W);
+    const int64_t t = m / W;
+    const int p = (int)(t % H), n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = p + dir * (r - 1);
+      if (ih < 0 || ih >= H) continue;
+      const float *xrow = x + ((int64_t)(n * H + ih) * W) * CG;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = q + dir * (s - 1);
+        if (iw < 0 || iw >= W) continue;
+        const float *wt = wsm + (size_t)((r * 3 + s) * CG) * K + ko * 8;
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+          const float xv = __ldg(xrow + (int64_t)iw * CG + c);
+          const float4 a = *reinterpret_cast<const float4 *>(wt + (size_t)c * K);
+          const float4 b = *reinterpret_cast<const float4 *>(wt + (size_t)c * K + 4);
+          acc[0] = fmaf(xv, a.x, acc[0]); acc[1] = fmaf(xv, a.y, acc[1]);
+          acc[2] = fmaf(xv, a.z, acc[2]); acc[3] = fmaf(xv, a.w, acc[3]);
+          acc[4] = fmaf(xv, b.x, acc[4]); acc[5] = fmaf(xv, b.y, acc[5]);
+          acc[6] = fmaf(xv, b.z, acc[6]); acc[7] = fmaf(xv, b.w, acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ko * 8 + j;
+      if (ep.bias) acc[j] += __ldg(ep.bias + k);
+      acc[j] = apply_act(acc[j], ep.act, ep.slope);
+      if (ep.chan_scale) acc[j] *= __ldg(ep.chan_scale + (int64_t)n * K + k);
+      if (ep.round_tf32) acc[j] = round_tf32(acc[j]);
+    }
+    float4 *dst = reinterpret_cast<float4 *>(y + m * K + ko * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// weight gradient with ONE dense channel (Cd == 1): stream the gathered tensor once (L lanes x float4 per pixel),
+// multiply by the 9 neighbouring dz scalars, keep 9 x 4 accumulators per lane; block partials -> atomicAdd.
+// dw[0][c][r][s] += sum_pix x[pix][c] * dz[pix + pad - (r,s)]      (mode 0, stride 1, pad 1)
+template <int L>
+__global__ void __launch_bounds__(256)
+conv3x3s1_wgrad_cd1_kernel(const float *__restrict__ x, const float *__restrict__ dz, float *__restrict__ dw, int N,
+                           int H, int W, int C, int64_t pix_per_block) {
+  __shared__ float red[9 * 128];  // C <= 128
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  constexpr int GROUPS = 32 / L;
+  const int lane = threadIdx.x & 31, sl = lane % L, sg = lane / L;
+  const int gid = (threadIdx.x >> 5) * GROUPS + sg;           // pixel lane within the block
+  const int gcount = (blockDim.x >> 5) * GROUPS;
+  const int64_t M = (int64_t)N * H * W;
+  const int64_t m0 = (int64_t)blockIdx.x * pix_per_block;
+  int64_t m1 = m0 + pix_per_block;
+  if (m1 > M) m1 = M;
+  const int c0 = sl * 4;
+  float4 acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c0 < C) {
+    for (int64_t m = m0 + gid; m < m1; m += gcount) {
+      const int w = (int)(m % W);
+      const int64_t t2 = m / W;
+      const int h = (int)(t2 % H);
+      const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + m * C + c0));
+      const float *dzc = dz + m;  // same (n,h,w) in the output grid (P == H, Q == W)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int oh = h + 1 - r;
+        if (oh < 0 || oh >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ow = w + 1 - s;
+          if (ow < 0 || ow >= W) continue;
+          const float d = __ldg(dzc + (1 - r) * W + (1 - s));
+          float4 &a = acc[r * 3 + s];
+          a.x = fmaf(xv.x, d, a.x); a.y = fmaf(xv.y, d, a.y); a.z = fmaf(xv.z, d, a.z); a.w = fmaf(xv.w, d, a.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      atomicAdd(&red[t * C + c0 + 0], acc[t].x);
+      atomicAdd(&red[t * C + c0 + 1], acc[t].y);
+      atomicAdd(&red[t * C + c0 + 2], acc[t].z);
+      atomicAdd(&red[t * C + c0 + 3], acc[t].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int c = i % C, t = i / C;
+    atomicAdd(dw + (int64_t)c * 9 + t, red[i]);  // dw[0][c][r][s], t = r*3+s
+  }
+}
+
 // column sums: out[c] += sum_m x[m][c]   (bias gradient). out zeroed by caller.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t M, int C,
@@ -531,7 +762,7 @@ static GatherP make_gather(int N, int H, int W, int C, int P, int Q, int R, int 
   GatherP g;
   g.N = N; g.H = H; g.W = W; g.C = C; g.P = P; g.Q = Q; g.R = R; g.S = S;
   g.stride = stride; g.pad_t = pad_t; g.pad_l = pad_l; g.pad_mode = pad_mode; g.up = up;
-  g.Hv = H * up; g.Wv = W * up; g.mode = mode;
+  g.Hv = H * up; g.Wv = W * up; g.mode = mode; g.cls = 1;
   return g;
 }
 
@@ -551,6 +782,34 @@ int simt_gather_gemm(int N, int H, int W, int C, int P, int Q, int K, int R, int
   int Ktot = R * S * C;
   size_t wbytes = (size_t)Ktot * K * sizeof(float);
   const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+  // lean 3x3 / stride 1 / pad 1 kernels (mode 0: conv fprop; mode 1: transposed gather with mirrored taps)
+  const bool s3 = R == 3 && S == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && up == 1 && pad_mode == B200GAN_PAD_ZERO &&
+                  P == H && Q == W && aligned;
+  const int dir = mode == 0 ? 1 : -1;
+  if (s3 && K <= 4 && C % 4 == 0 && C >= 16 && C <= 512 && wbytes <= 48 * 1024) {
+    const int L = C >= 128 ? 32 : (C >= 64 ? 16 : (C >= 32 ? 8 : 4));
+    const int64_t ngroups = (int64_t)N * H * ((W + 3) / 4);
+    int64_t blocks = ceil_div64(ngroups, 8 * (32 / L));
+    if (blocks > 148 * 16) blocks = 148 * 16;
+#define LAUNCH_SK(LL, KK_) conv3x3s1_smallk_kernel<LL, KK_><<<(unsigned)blocks, 256, wbytes, st>>>(x, wp, y, e, N, H, W, C, dir)
+#define LAUNCH_SK_L(KK_) \
+  do { if (L == 32) LAUNCH_SK(32, KK_); else if (L == 16) LAUNCH_SK(16, KK_); else if (L == 8) LAUNCH_SK(8, KK_); else LAUNCH_SK(4, KK_); } while (0)
+    if (K == 1) LAUNCH_SK_L(1); else if (K == 2) LAUNCH_SK_L(2); else if (K == 3) LAUNCH_SK_L(3); else LAUNCH_SK_L(4);
+#undef LAUNCH_SK_L
+#undef LAUNCH_SK
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
+  if (s3 && C <= 4 && K % 8 == 0 && wbytes <= 48 * 1024) {
+    int64_t blocks = ceil_div64(M * (K / 8), 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (C == 1) conv3x3s1_smallc_kernel<1><<<(unsigned)blocks, 256, wbytes, st>>>(x, wp, y, e, N, H, W, K, dir);
+    else if (C == 2) conv3x3s1_smallc_kernel<2><<<(unsigned)blocks, 256, wbytes, st>>>(x, wp, y, e, N, H, W, K, dir);
+    else if (C == 3) conv3x3s1_smallc_kernel<3><<<(unsigned)blocks, 256, wbytes, st>>>(x, wp, y, e, N, H, W, K, dir);
+    else conv3x3s1_smallc_kernel<4><<<(unsigned)blocks, 256, wbytes, st>>>(x, wp, y, e, N, H, W, K, dir);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   if (K <= 4 && C % 4 == 0 && C >= 16 && wbytes <= 48 * 1024 && aligned) {
     // few output channels: lanes over channels (float4), several pixels in flight per lane group
     const int64_t blocks_max = 148 * 8;
@@ -580,8 +839,15 @@ int simt_gather_gemm(int N, int H, int W, int C, int P, int Q, int K, int R, int
     if (blocks > 148 * 32) blocks = 148 * 32;
     conv_smallc_kernel<<<(unsigned)blocks, 256, wbytes, st>>>(g, e, x, wp, y, K);
   } else {
-    dim3 grid((unsigned)ceil_div64(M, FBM), (unsigned)ceil_div(K, FBN));
-    conv_gather_gemm_kernel<<<grid, 256, 0, st>>>(g, e, x, wp, y, K);
+    if (mode == 1 && stride > 1 && stride <= 4) {
+      g.cls = stride;
+      int64_t mc = (int64_t)N * ceil_div(P, stride) * ceil_div(Q, stride);
+      dim3 grid((unsigned)ceil_div64(mc, FBM), (unsigned)ceil_div(K, FBN), (unsigned)(stride * stride));
+      conv_gather_gemm_kernel<<<grid, 256, 0, st>>>(g, e, x, wp, y, K);
+    } else {
+      dim3 grid((unsigned)ceil_div64(M, FBM), (unsigned)ceil_div(K, FBN));
+      conv_gather_gemm_kernel<<<grid, 256, 0, st>>>(g, e, x, wp, y, K);
+    }
   }
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
@@ -596,6 +862,20 @@ int simt_wgrad(int N, int H, int W, int Cg, int P, int Q, int Cd, int R, int S, 
   int Ktot = R * S * Cg;
   B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)Ktot * Cd * sizeof(float), st));
   if (M == 0) return B200GAN_OK;
+  if (Cd == 1 && R == 3 && S == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && up == 1 && pad_mode == B200GAN_PAD_ZERO &&
+      P == H && Q == W && Cg % 4 == 0 && Cg >= 16 && Cg <= 128 && ((uintptr_t)xg % 16 == 0)) {
+    const int L = Cg >= 128 ? 32 : (Cg >= 64 ? 16 : (Cg >= 32 ? 8 : 4));
+    int64_t blocks = 148 * 4;
+    int64_t ppb = ceil_div64(M, blocks);
+    if (ppb < 256) ppb = 256;
+    blocks = ceil_div64(M, ppb);
+    if (L == 32) conv3x3s1_wgrad_cd1_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(xg, dn, dw, N, H, W, Cg, ppb);
+    else if (L == 16) conv3x3s1_wgrad_cd1_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(xg, dn, dw, N, H, W, Cg, ppb);
+    else if (L == 8) conv3x3s1_wgrad_cd1_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(xg, dn, dw, N, H, W, Cg, ppb);
+    else conv3x3s1_wgrad_cd1_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(xg, dn, dw, N, H, W, Cg, ppb);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   if (Cd <= 4) {
     int yb = ceil_div(Ktot, 256);
     int64_t xb = (148 * 8) / yb;

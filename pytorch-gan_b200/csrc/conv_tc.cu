@@ -23,6 +23,7 @@
 // two CTAs are resident per SM so one CTA's epilogue overlaps the other's main loop.
 #include "tc_common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace b200gan {
 
@@ -91,8 +92,7 @@ struct TcParams {
   int32_t bw_log2, bh_log2;  // box width / height (powers of two), BW*BH*BNn = 128
   int32_t tiles_w, tiles_h;
   int32_t N, Ho, Wo;         // logical output grid of one phase
-  int64_t out_off[4];        // element offset of a phase's (0,0,0) output pixel
-  int64_t sn, sh, sw;        // output strides in elements
+  int32_t out_dc[4], out_da[4];  // per phase: channel base / phase-row coordinate in the output tensor map
   int32_t ldk;               // channels of the output tensor (row length)
   const float *bias;
   const float *chan_scale;
@@ -101,7 +101,13 @@ struct TcParams {
   float slope;
   int32_t rtf;
   float *y;
+  long long *trace;  // bring-up: per-CTA clock64 timeline (64 slots per CTA) or nullptr
 };
+
+#define TC_TRACE(slot)                                                   \
+  do {                                                                   \
+    if (p.trace) p.trace[((size_t)blockIdx.z * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
@@ -120,7 +126,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ TcParams p) {
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * TC_BK * 4;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -145,9 +151,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tap0 = p.tap_begin[ph];
   const int iters = (p.tap_begin[ph + 1] - tap0) * p.kchunks;
 
+  if (threadIdx.x == 0) TC_TRACE(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -160,6 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 0) TC_TRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -172,6 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t *sa = smem + stage * STAGE_BYTES;
         uint8_t *sb = sa + TC_A_BYTES;
         const TcTap tp = p.taps[tap0 + tap];
+        if (it < 16) TC_TRACE(2 + it);
         mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
         tma_load_5d(sa, &tmA, &full[stage], tp.dc + kc * TC_BK, w0 + tp.dw, tp.da, h0 + tp.dh, n0);
         tma_load_2d(sb, &tmB, &full[stage], kc * TC_BK, (tap0 + tap) * p.kout_total + ntile * BN);
@@ -194,6 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int it = 0; it < iters; ++it) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (it < 16) TC_TRACE(20 + it);
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
@@ -212,6 +223,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp & 3) =====
+    // TMEM -> registers -> (bias, activation, Dropout2d scale, TF32 rounding, BN partial sums) -> shared memory in
+    // the 128B-swizzled box layout -> TMA bulk tensor store.  The pipeline buffers are free once tmem_full fired
+    // (every MMA has retired), so the staging tile reuses them: chunk c (32 channels) at smem + c * 16 KB.
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int lw = m & (BW - 1);
@@ -219,28 +233,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ln = m >> (p.bw_log2 + p.bh_log2);
     const int ow = w0 + lw, oh = h0 + lh, on = n0 + ln;
     const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
-    float *yrow = p.y + p.out_off[ph] + (int64_t)on * p.sn + (int64_t)oh * p.sh + (int64_t)ow * p.sw + ntile * BN;
     const float *cs = p.chan_scale ? p.chan_scale + (int64_t)on * p.ldk + ntile * BN : nullptr;
+    const int act = p.act, rtf = p.rtf;
+    const float slope = p.slope;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TC_TRACE(40);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       float v[32];
+      if (threadIdx.x == 64) TC_TRACE(48 + (c >> 5) * 3);
       tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (threadIdx.x == 64) TC_TRACE(49 + (c >> 5) * 3);
+      // every option is tested ONCE per chunk, never per element: a switch inside the unrolled element loop
+      // becomes 32 indirect branches into a 50 KB body and costs ~200 cycles each (measured: 6.5k cycles/chunk)
+      if (p.bias) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + ntile * BN + c);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float o = v[j];
-        if (p.bias) o += __ldg(p.bias + ntile * BN + c + j);
-        o = apply_act(o, p.act, p.slope);
-        if (cs && valid) o *= __ldg(cs + c + j);
-        if (p.rtf) o = round_tf32(o);
-        v[j] = o;
+        for (int j = 0; j < 8; ++j) {
+          float4 b = __ldg(b4 + j);
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
       }
-      if (valid) {
-        float4 *dst = reinterpret_cast<float4 *>(yrow + c);
+      if (act == B200GAN_ACT_LRELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+      } else if (act == B200GAN_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (act == B200GAN_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+      } else if (act == B200GAN_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
       }
+      if (cs && valid) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(cs + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 b = __ldg(s4 + j);
+          v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w;
+        }
+      }
+      if (rtf) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+      }
+      {
+        uint8_t *row = smem + (c >> 5) * TC_A_BYTES + m * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4 *>(row + ((j ^ (m & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (threadIdx.x == 64) TC_TRACE(50 + (c >> 5) * 3);
       if (p.stats) {
         float s2[32];
 #pragma unroll
@@ -254,8 +301,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         red[(q * BN + c + lane) * 2 + 1] = cs2;
       }
     }
+    if (threadIdx.x == 64) TC_TRACE(43);
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the async (TMA) proxy
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      TC_TRACE(44);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32)
+        tma_store_5d(&tmY, smem + (c >> 5) * TC_A_BYTES, p.out_dc[ph] + ntile * BN + c, w0, p.out_da[ph], h0, n0);
+      TC_TRACE(45);
+      tma_store_commit_and_wait_read();
+    }
     if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 64;
       if (e < BN) {
         float a = 0.f, b = 0.f;
@@ -269,12 +326,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
+  if (threadIdx.x == 64) TC_TRACE(41);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc<BN>(tmem);
   }
+  if (threadIdx.x == 0) TC_TRACE(42);
 }
 
 // ---- host ----------------------------------------------------------------------------------------
@@ -285,14 +344,15 @@ static int ilog2_ceil(int v) {
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t st) {
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmY, const TcParams &p, dim3 grid,
+                     cudaStream_t st) {
   constexpr int SMEM = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + 4 * BN * 2 * 4;
   static bool attr_done = false;
   if (!attr_done) {
     B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
-  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, p);
+  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, tmY, p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
@@ -319,10 +379,12 @@ int tc_supported(const b200gan_conv_geom *g, int pass) {
 // Shared by fprop and dgrad.
 //  in      : contracted activation tensor [N][Hi][Wi][Cc] (x for fprop, dy for dgrad)
 //  phase_in: 1 -> `in` is addressed through the phase view {2Cc, Wi/2, 2, Hi/2, N} (dgrad of UP2)
-//  out grid: N x Ho x Wo pixels per phase, written with strides (sn, sh, sw) at out_off[phase]
+//  out     : N x Ho x Wo pixels per phase.  phase_out: 1 -> y is the full-resolution tensor [N][2Ho][2Wo][ldk]
+//            addressed through the phase view {2*ldk, Wo, 2, Ho, N}; phase z writes (out_dc[z], out_da[z]).
 static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in, const float *packedB, int Kout,
-                  int nphase, const int *tap_begin, const TcTap *taps, int Ho, int Wo, const int64_t *out_off,
-                  int64_t sn, int64_t sh, int64_t sw, int ldk, const b200gan_epilogue *ep, float *y, cudaStream_t st) {
+                  int nphase, const int *tap_begin, const TcTap *taps, int Ho, int Wo, bool phase_out,
+                  const int *out_dc, const int *out_da, int ldk, const b200gan_epilogue *ep, float *y,
+                  cudaStream_t st) {
   const int BN = (Kout % 128 == 0) ? 128 : 64;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -343,10 +405,10 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   p.N = N;
   p.Ho = Ho;
   p.Wo = Wo;
-  for (int i = 0; i < 4; ++i) p.out_off[i] = i < nphase ? out_off[i] : 0;
-  p.sn = sn;
-  p.sh = sh;
-  p.sw = sw;
+  for (int i = 0; i < 4; ++i) {
+    p.out_dc[i] = i < nphase ? out_dc[i] : 0;
+    p.out_da[i] = i < nphase ? out_da[i] : 0;
+  }
   p.ldk = ldk;
   p.bias = ep ? ep->bias : nullptr;
   p.chan_scale = ep ? ep->chan_scale : nullptr;
@@ -355,10 +417,28 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   p.slope = ep ? ep->slope : 0.f;
   p.rtf = ep ? ep->round_tf32 : 0;
   p.y = y;
+  p.trace = nullptr;
+  if (const char *tv = getenv("B200GAN_TC_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(tv, nullptr, 0));
   B2_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)packedB % 16 == 0) && ((uintptr_t)y % 16 == 0),
                "tcgen05 conv: pointers must be 16-byte aligned");
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
+  {
+    // output map: box = one 32-channel chunk of the 128-pixel tile; TMA clips rows outside the tensor
+    uint64_t dims[5], strides[4];
+    uint32_t box[5] = {TC_BK, (uint32_t)BW, 1, (uint32_t)BH, (uint32_t)BNn};
+    const uint64_t L = (uint64_t)ldk;
+    if (!phase_out) {
+      dims[0] = L; dims[1] = Wo; dims[2] = 1; dims[3] = Ho; dims[4] = N;
+      strides[0] = L * 4; strides[1] = (uint64_t)Wo * L * 4; strides[2] = (uint64_t)Wo * L * 4;
+      strides[3] = (uint64_t)Ho * Wo * L * 4;
+    } else {
+      dims[0] = 2 * L; dims[1] = Wo; dims[2] = 2; dims[3] = Ho; dims[4] = N;
+      strides[0] = 2 * L * 4; strides[1] = (uint64_t)2 * Wo * L * 4; strides[2] = (uint64_t)4 * Wo * L * 4;
+      strides[3] = (uint64_t)4 * Ho * Wo * L * 4;
+    }
+    if (int e = make_tmap_f32(&tmY, y, 5, dims, strides, box)) return e;
+  }
   {
     uint64_t dims[5], strides[4];
     uint32_t box[5] = {TC_BK, (uint32_t)BW, 1, (uint32_t)BH, (uint32_t)BNn};
@@ -384,8 +464,8 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
     if (int e = make_tmap_f32(&tmB, packedB, 2, dims, strides, box)) return e;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)nphase);
-  if (BN == 128) return launch_tc<128, 3>(tmA, tmB, p, grid, st);
-  return launch_tc<64, 4>(tmA, tmB, p, grid, st);
+  if (BN == 128) return launch_tc<128, 3>(tmA, tmB, tmY, p, grid, st);
+  return launch_tc<64, 4>(tmA, tmB, tmY, p, grid, st);
 }
 
 int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
@@ -393,14 +473,13 @@ int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float
   TcTap taps[TC_MAX_TAPS];
   memset(taps, 0, sizeof(taps));
   int tap_begin[5] = {0, 0, 0, 0, 0};
-  int64_t out_off[4] = {0, 0, 0, 0};
+  int out_dc[4] = {0, 0, 0, 0}, out_da[4] = {0, 0, 0, 0};
   b200gan_epilogue e2;
   if (ep) {
     e2 = *ep;
     // per-sample (InstanceNorm) sums can only be fused when a tile never spans two images
     if (e2.stats && e2.stats_per_sample) B2_UNSUPPORTED("tcgen05 fprop: per-sample statistics are not fused");
   }
-  const int64_t K = g->K;
   if (g->up == 2) {
     // phase (a,b): out[2i+a][2j+b] = sum_{dr,ds} x[i+a-1+dr][j+b-1+ds] * Wf[a][b][dr][ds]
     for (int ph = 0; ph < 4; ++ph) {
@@ -411,11 +490,12 @@ int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float
         TcTap &t = taps[ph * 4 + tp];
         t.dc = 0; t.dw = (int8_t)(b - 1 + ds); t.da = 0; t.dh = (int8_t)(a - 1 + dr);
       }
-      out_off[ph] = ((int64_t)a * g->Q + b) * K;
+      out_dc[ph] = b * g->K;
+      out_da[ph] = a;
     }
     tap_begin[4] = 16;
-    return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 4, tap_begin, taps, g->H, g->W, out_off,
-                  (int64_t)g->P * g->Q * K, (int64_t)2 * g->Q * K, (int64_t)2 * K, g->K, ep ? &e2 : nullptr, y, st);
+    return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 4, tap_begin, taps, g->H, g->W, true, out_dc, out_da,
+                  g->K, ep ? &e2 : nullptr, y, st);
   }
   int nt = 0;
   for (int r = 0; r < g->R; ++r)
@@ -424,16 +504,15 @@ int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float
       t.dc = 0; t.dw = (int8_t)(s - g->pad_l); t.da = 0; t.dh = (int8_t)(r - g->pad_t);
     }
   tap_begin[1] = nt;
-  return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 1, tap_begin, taps, g->P, g->Q, out_off,
-                (int64_t)g->P * g->Q * K, (int64_t)g->Q * K, K, g->K, ep ? &e2 : nullptr, y, st);
+  return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 1, tap_begin, taps, g->P, g->Q, false, out_dc, out_da,
+                g->K, ep ? &e2 : nullptr, y, st);
 }
 
 int tc_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, float *dx, cudaStream_t st) {
   TcTap taps[TC_MAX_TAPS];
   memset(taps, 0, sizeof(taps));
   int tap_begin[5] = {0, 0, 0, 0, 0};
-  int64_t out_off[4] = {0, 0, 0, 0};
-  const int64_t C = g->C;
+  int out_dc[4] = {0, 0, 0, 0}, out_da[4] = {0, 0, 0, 0};
   if (g->up == 2) {
     // dx[i][j] = sum_{a,b,dr,ds} dy[2(i-(a-1+dr))+a][2(j-(b-1+ds))+b] * Wf[a][b][dr][ds]^T
     for (int ph = 0; ph < 4; ++ph) {
@@ -445,8 +524,8 @@ int tc_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, f
       }
     }
     tap_begin[1] = 16;
-    return run_tc(dy, g->N, g->P, g->Q, g->K, true, packed, g->C, 1, tap_begin, taps, g->H, g->W, out_off,
-                  (int64_t)g->H * g->W * C, (int64_t)g->W * C, C, g->C, nullptr, dx, st);
+    return run_tc(dy, g->N, g->P, g->Q, g->K, true, packed, g->C, 1, tap_begin, taps, g->H, g->W, false, out_dc, out_da,
+                  g->C, nullptr, dx, st);
   }
   int nt = 0;
   for (int r = 0; r < g->R; ++r)
@@ -455,8 +534,8 @@ int tc_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, f
       t.dc = 0; t.dw = (int8_t)(g->pad_l - s); t.da = 0; t.dh = (int8_t)(g->pad_t - r);
     }
   tap_begin[1] = nt;
-  return run_tc(dy, g->N, g->P, g->Q, g->K, false, packed, g->C, 1, tap_begin, taps, g->H, g->W, out_off,
-                (int64_t)g->H * g->W * C, (int64_t)g->W * C, C, g->C, nullptr, dx, st);
+  return run_tc(dy, g->N, g->P, g->Q, g->K, false, packed, g->C, 1, tap_begin, taps, g->H, g->W, false, out_dc, out_da,
+                g->C, nullptr, dx, st);
 }
 
 }  // namespace b200gan

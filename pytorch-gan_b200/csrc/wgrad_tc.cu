@@ -49,7 +49,7 @@ struct WgParams {
 template <int NB, int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                const __grid_constant__ WgParams p) {
+                const __grid_constant__ CUtensorMap tmP, const __grid_constant__ WgParams p) {
   constexpr int A_BYTES = 4 * WG_CHUNK_BYTES;            // 128 channels
   constexpr int B_BYTES = (NB / 32) * WG_CHUNK_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -147,9 +147,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       umma_commit(tmem_full);
     }
   } else {
+    // TMEM -> registers -> 128B-swizzled staging tile in the (now idle) pipeline buffers -> TMA store of the
+    // partial tile into partial[split][job][m'][n'] (a 2-D tensor map over [rows][ldn]).
     const int q = warp & 3;
     const int m = q * 32 + lane;  // row of the 128 x NB tile
-    float *dst = p.partial + (((int64_t)split * p.njobs + job) * p.mtotal + (mt * 128 + m)) * p.ldn + nt * NB;
     if (iters > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
@@ -163,9 +164,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      float4 *d4 = reinterpret_cast<float4 *>(dst + c);
+      uint8_t *row = smem + (c >> 5) * 16384 + m * 128;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4 *>(row + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      const int row0 = (split * p.njobs + job) * p.mtotal + mt * 128;
+#pragma unroll 1
+      for (int c = 0; c < NB; c += 32) tma_store_2d(&tmP, smem + (c >> 5) * 16384, nt * NB + c, row0);
+      tma_store_commit_and_wait_read();
     }
   }
   tc_fence_before();
@@ -277,14 +287,15 @@ size_t tc_wgrad_workspace_floats(const b200gan_conv_geom *g) {
 }
 
 template <int NB, int STAGES>
-static int launch_wg(const CUtensorMap &tmX, const CUtensorMap &tmY, const WgParams &p, dim3 grid, cudaStream_t st) {
+static int launch_wg(const CUtensorMap &tmX, const CUtensorMap &tmY, const CUtensorMap &tmP, const WgParams &p, dim3 grid,
+                     cudaStream_t st) {
   constexpr int SMEM = STAGES * (4 + NB / 32) * WG_CHUNK_BYTES + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
-  wgrad_tc_kernel<NB, STAGES><<<grid, WG_THREADS, SMEM, st>>>(tmX, tmY, p);
+  wgrad_tc_kernel<NB, STAGES><<<grid, WG_THREADS, SMEM, st>>>(tmX, tmY, tmP, p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
@@ -344,8 +355,15 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
     }
     if (int e = make_tmap_f32(&tmY, dy, 5, dims, strides, box, 1)) return e;
   }
+  CUtensorMap tmP;
+  {
+    uint64_t dims[2] = {(uint64_t)pl.ldn, (uint64_t)pl.nsplits * pl.njobs * pl.mtotal};
+    uint64_t strides[1] = {(uint64_t)pl.ldn * 4};
+    uint32_t pbox[2] = {32, 128};
+    if (int e = make_tmap_f32(&tmP, ws, 2, dims, strides, pbox)) return e;
+  }
   dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
-  int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, p, grid, st) : launch_wg<64, 4>(tmX, tmY, p, grid, st);
+  int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, tmP, p, grid, st) : launch_wg<64, 4>(tmX, tmY, tmP, p, grid, st);
   if (rc) return rc;
   WgReduceP rp;
   rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.nsplits = pl.nsplits; rp.njobs = pl.njobs;
