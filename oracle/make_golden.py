@@ -206,8 +206,102 @@ def golden_wgan_gp(img_size=32, batch=64, seed=0):
           f"bias grads zero: {fix['bias_grads_zero']}; wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def _import_reference_module(rel, name):
+    """Import implementations/<rel> (pix2pix/models.py, cyclegan/models.py are side-effect free) under a unique name."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "implementations", rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _slim(t, step=8):
+    return t[..., ::step, ::step].clone() if t.dim() == 4 else t.clone()
+
+
+def _grad_norms(model):
+    return {k: p.grad.double().norm().item() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def golden_pix2pix(seed=0, size=256, batch=1):
+    """pix2pix/models.py: GeneratorUNet + Discriminator, forward + backward of the script's G loss
+    (pix2pix.py:141-150: MSE(D(fake_B, real_A), valid) + 100 * L1(fake_B, real_B)); dropout off (eval)."""
+    ref = _import_reference_module("pix2pix/models.py", "ref_pix2pix_models")
+    torch.manual_seed(seed)
+    g_ref, d_ref = ref.GeneratorUNet(), ref.Discriminator()
+    g_ref.apply(ref.weights_init_normal)
+    d_ref.apply(ref.weights_init_normal)
+    g_or, d_or = ref_models.build_pix2pix(seed)
+    _assert_same_state(g_ref, g_or, "pix2pix G")
+    _assert_same_state(d_ref, d_or, "pix2pix D")
+    real_a = ref_models.synthetic_images(batch, 3, size, size, seed=seed + 1)
+    real_b = ref_models.synthetic_images(batch, 3, size, size, seed=seed + 2)
+    out = {}
+    for tag, (g, d) in {"ref": (g_ref, d_ref), "oracle": (g_or, d_or)}.items():
+        g.eval()  # Dropout(0.5) off; InstanceNorm keeps instance statistics in eval mode (no running stats)
+        d.train()
+        g.zero_grad(); d.zero_grad()
+        fake_b = g(real_a)
+        pred = d(fake_b, real_a)
+        loss = torch.nn.MSELoss()(pred, torch.ones_like(pred)) + 100 * torch.nn.L1Loss()(fake_b, real_b)
+        loss.backward()
+        out[tag] = dict(fake_b=fake_b.detach(), pred=pred.detach(), loss=loss.detach(), gn=_grad_norms(g), dn=_grad_norms(d))
+    r, o = out["ref"], out["oracle"]
+    assert torch.equal(r["fake_b"], o["fake_b"]) and torch.equal(r["pred"], o["pred"]) and torch.equal(r["loss"], o["loss"])
+    assert r["gn"] == o["gn"] and r["dn"] == o["dn"]
+    fix = dict(seed=seed, size=size, batch=batch, fake_b=_slim(r["fake_b"]), pred=r["pred"], loss=r["loss"],
+               g_grad_norms=r["gn"], d_grad_norms=r["dn"], torch_version=torch.__version__,
+               reference="pix2pix/models.py@36d3c77")
+    path = os.path.join(GOLD, f"pix2pix_{size}_b{batch}.pt")
+    torch.save(fix, path)
+    print(f"pix2pix {size}x{size} b{batch}: oracle == reference (bit-exact); wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def golden_cyclegan(seed=0, size=64, batch=2, blocks=9):
+    """cyclegan/models.py: GeneratorResNet + Discriminator; generator-side losses of cyclegan.py:177-204
+    (identity, GAN, cycle) on seeded images."""
+    ref = _import_reference_module("cyclegan/models.py", "ref_cyclegan_models")
+    shape = (3, size, size)
+    torch.manual_seed(seed)
+    nets_ref = [ref.GeneratorResNet(shape, blocks), ref.GeneratorResNet(shape, blocks), ref.Discriminator(shape),
+                ref.Discriminator(shape)]
+    for m in nets_ref:
+        m.apply(ref.weights_init_normal)
+    nets_or = list(ref_models.build_cyclegan(shape, blocks, seed))
+    for a, b, nm in zip(nets_ref, nets_or, ("G_AB", "G_BA", "D_A", "D_B")):
+        _assert_same_state(a, b, "cyclegan " + nm)
+    real_a = ref_models.synthetic_images(batch, 3, size, size, seed=seed + 1)
+    real_b = ref_models.synthetic_images(batch, 3, size, size, seed=seed + 2)
+    mse, l1 = torch.nn.MSELoss(), torch.nn.L1Loss()
+    out = {}
+    for tag, (g_ab, g_ba, d_a, d_b) in {"ref": nets_ref, "oracle": nets_or}.items():
+        for m in (g_ab, g_ba, d_a, d_b):
+            m.train()
+            m.zero_grad()
+        valid = torch.ones(batch, *d_a.output_shape)
+        loss_id = (l1(g_ba(real_a), real_a) + l1(g_ab(real_b), real_b)) / 2          # cyclegan.py:180-183
+        fake_b = g_ab(real_a)
+        fake_a = g_ba(real_b)
+        loss_gan = (mse(d_b(fake_b), valid) + mse(d_a(fake_a), valid)) / 2            # :186-191
+        loss_cyc = (l1(g_ba(fake_b), real_a) + l1(g_ab(fake_a), real_b)) / 2          # :194-199
+        loss_g = loss_gan + 10.0 * loss_cyc + 5.0 * loss_id                           # :202
+        loss_g.backward()
+        out[tag] = dict(fake_b=fake_b.detach(), fake_a=fake_a.detach(), loss_g=loss_g.detach(),
+                        parts=(loss_id.item(), loss_gan.item(), loss_cyc.item()), gn=_grad_norms(g_ab), gn2=_grad_norms(g_ba))
+    r, o = out["ref"], out["oracle"]
+    assert torch.equal(r["fake_b"], o["fake_b"]) and torch.equal(r["loss_g"], o["loss_g"]) and r["gn"] == o["gn"]
+    fix = dict(seed=seed, size=size, batch=batch, blocks=blocks, fake_b=_slim(r["fake_b"], 4), fake_a=_slim(r["fake_a"], 4),
+               loss_g=r["loss_g"], parts=r["parts"], g_ab_grad_norms=r["gn"], g_ba_grad_norms=r["gn2"],
+               torch_version=torch.__version__, reference="cyclegan/models.py@36d3c77")
+    path = os.path.join(GOLD, f"cyclegan_{size}_b{batch}.pt")
+    torch.save(fix, path)
+    print(f"cyclegan {size}x{size} b{batch}: oracle == reference (bit-exact); wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     golden_dcgan(32, 8)
     golden_ops()
     golden_wgan_gp()
+    golden_pix2pix()
+    golden_cyclegan()

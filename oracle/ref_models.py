@@ -170,3 +170,191 @@ def compute_gradient_penalty(D, real_samples, fake_samples, alpha):
 def synthetic_alpha(n, seed=0):
     rng = np.random.RandomState(seed)
     return torch.tensor(rng.random_sample((n, 1, 1, 1)), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# Pix2Pix (BASELINE config 3) and CycleGAN (config 4), stock torch.nn
+# ------------------------------------------------------------------------------------------------
+def weights_init_normal_cyclegan(m):
+    # cyclegan/models.py:6-14 (conv biases zeroed as well)
+    classname = m.__class__.__name__
+    if classname.find("Conv") != -1:
+        torch.nn.init.normal_(m.weight.data, 0.0, 0.02)
+        if hasattr(m, "bias") and m.bias is not None:
+            torch.nn.init.constant_(m.bias.data, 0.0)
+    elif classname.find("BatchNorm2d") != -1:
+        torch.nn.init.normal_(m.weight.data, 1.0, 0.02)
+        torch.nn.init.constant_(m.bias.data, 0.0)
+
+
+class UNetDown(nn.Module):
+    # pix2pix/models.py:20-32
+    def __init__(self, in_size, out_size, normalize=True, dropout=0.0):
+        super().__init__()
+        layers = [nn.Conv2d(in_size, out_size, 4, 2, 1, bias=False)]
+        if normalize:
+            layers.append(nn.InstanceNorm2d(out_size))
+        layers.append(nn.LeakyReLU(0.2))
+        if dropout:
+            layers.append(nn.Dropout(dropout))
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class UNetUp(nn.Module):
+    # pix2pix/models.py:35-52
+    def __init__(self, in_size, out_size, dropout=0.0):
+        super().__init__()
+        layers = [nn.ConvTranspose2d(in_size, out_size, 4, 2, 1, bias=False), nn.InstanceNorm2d(out_size),
+                  nn.ReLU(inplace=True)]
+        if dropout:
+            layers.append(nn.Dropout(dropout))
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x, skip_input):
+        return torch.cat((self.model(x), skip_input), 1)
+
+
+class GeneratorUNet(nn.Module):
+    # pix2pix/models.py:55-101
+    def __init__(self, in_channels=3, out_channels=3):
+        super().__init__()
+        self.down1 = UNetDown(in_channels, 64, normalize=False)
+        self.down2 = UNetDown(64, 128)
+        self.down3 = UNetDown(128, 256)
+        self.down4 = UNetDown(256, 512, dropout=0.5)
+        self.down5 = UNetDown(512, 512, dropout=0.5)
+        self.down6 = UNetDown(512, 512, dropout=0.5)
+        self.down7 = UNetDown(512, 512, dropout=0.5)
+        self.down8 = UNetDown(512, 512, normalize=False, dropout=0.5)
+        self.up1 = UNetUp(512, 512, dropout=0.5)
+        self.up2 = UNetUp(1024, 512, dropout=0.5)
+        self.up3 = UNetUp(1024, 512, dropout=0.5)
+        self.up4 = UNetUp(1024, 512, dropout=0.5)
+        self.up5 = UNetUp(1024, 256)
+        self.up6 = UNetUp(512, 128)
+        self.up7 = UNetUp(256, 64)
+        self.final = nn.Sequential(nn.Upsample(scale_factor=2), nn.ZeroPad2d((1, 0, 1, 0)),
+                                   nn.Conv2d(128, out_channels, 4, padding=1), nn.Tanh())
+
+    def forward(self, x):
+        d1 = self.down1(x)
+        d2 = self.down2(d1)
+        d3 = self.down3(d2)
+        d4 = self.down4(d3)
+        d5 = self.down5(d4)
+        d6 = self.down6(d5)
+        d7 = self.down7(d6)
+        d8 = self.down8(d7)
+        u1 = self.up1(d8, d7)
+        u2 = self.up2(u1, d6)
+        u3 = self.up3(u2, d5)
+        u4 = self.up4(u3, d4)
+        u5 = self.up5(u4, d3)
+        u6 = self.up6(u5, d2)
+        u7 = self.up7(u6, d1)
+        return self.final(u7)
+
+
+class Pix2PixDiscriminator(nn.Module):
+    # pix2pix/models.py:109-133
+    def __init__(self, in_channels=3):
+        super().__init__()
+
+        def block(i, o, normalization=True):
+            layers = [nn.Conv2d(i, o, 4, stride=2, padding=1)]
+            if normalization:
+                layers.append(nn.InstanceNorm2d(o))
+            layers.append(nn.LeakyReLU(0.2, inplace=True))
+            return layers
+
+        self.model = nn.Sequential(*block(in_channels * 2, 64, normalization=False), *block(64, 128), *block(128, 256),
+                                   *block(256, 512), nn.ZeroPad2d((1, 0, 1, 0)),
+                                   nn.Conv2d(512, 1, 4, padding=1, bias=False))
+
+    def forward(self, img_A, img_B):
+        return self.model(torch.cat((img_A, img_B), 1))
+
+
+def build_pix2pix(seed=0):
+    """pix2pix.py:60-61,75-76: GeneratorUNet(), Discriminator(), then .apply(weights_init_normal)."""
+    torch.manual_seed(seed)
+    g, d = GeneratorUNet(), Pix2PixDiscriminator()
+    g.apply(weights_init_normal)
+    d.apply(weights_init_normal)
+    return g, d
+
+
+class ResidualBlock(nn.Module):
+    # cyclegan/models.py:22-37
+    def __init__(self, in_features):
+        super().__init__()
+        self.block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(in_features, in_features, 3),
+                                   nn.InstanceNorm2d(in_features), nn.ReLU(inplace=True), nn.ReflectionPad2d(1),
+                                   nn.Conv2d(in_features, in_features, 3), nn.InstanceNorm2d(in_features))
+
+    def forward(self, x):
+        return x + self.block(x)
+
+
+class GeneratorResNet(nn.Module):
+    # cyclegan/models.py:40-87
+    def __init__(self, input_shape, num_residual_blocks):
+        super().__init__()
+        channels = input_shape[0]
+        out_features = 64
+        model = [nn.ReflectionPad2d(channels), nn.Conv2d(channels, out_features, 7), nn.InstanceNorm2d(out_features),
+                 nn.ReLU(inplace=True)]
+        in_features = out_features
+        for _ in range(2):
+            out_features *= 2
+            model += [nn.Conv2d(in_features, out_features, 3, stride=2, padding=1), nn.InstanceNorm2d(out_features),
+                      nn.ReLU(inplace=True)]
+            in_features = out_features
+        for _ in range(num_residual_blocks):
+            model += [ResidualBlock(out_features)]
+        for _ in range(2):
+            out_features //= 2
+            model += [nn.Upsample(scale_factor=2), nn.Conv2d(in_features, out_features, 3, stride=1, padding=1),
+                      nn.InstanceNorm2d(out_features), nn.ReLU(inplace=True)]
+            in_features = out_features
+        model += [nn.ReflectionPad2d(channels), nn.Conv2d(out_features, channels, 7), nn.Tanh()]
+        self.model = nn.Sequential(*model)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class CycleGANDiscriminator(nn.Module):
+    # cyclegan/models.py:95-122
+    def __init__(self, input_shape):
+        super().__init__()
+        channels, height, width = input_shape
+        self.output_shape = (1, height // 2 ** 4, width // 2 ** 4)
+
+        def block(i, o, normalize=True):
+            layers = [nn.Conv2d(i, o, 4, stride=2, padding=1)]
+            if normalize:
+                layers.append(nn.InstanceNorm2d(o))
+            layers.append(nn.LeakyReLU(0.2, inplace=True))
+            return layers
+
+        self.model = nn.Sequential(*block(channels, 64, normalize=False), *block(64, 128), *block(128, 256),
+                                   *block(256, 512), nn.ZeroPad2d((1, 0, 1, 0)), nn.Conv2d(512, 1, 4, padding=1))
+
+    def forward(self, img):
+        return self.model(img)
+
+
+def build_cyclegan(input_shape=(3, 64, 64), n_residual_blocks=9, seed=0):
+    """cyclegan.py:59-62,80-83: G_AB, G_BA, D_A, D_B constructed in this order, then init in this order."""
+    torch.manual_seed(seed)
+    g_ab = GeneratorResNet(input_shape, n_residual_blocks)
+    g_ba = GeneratorResNet(input_shape, n_residual_blocks)
+    d_a = CycleGANDiscriminator(input_shape)
+    d_b = CycleGANDiscriminator(input_shape)
+    for m in (g_ab, g_ba, d_a, d_b):
+        m.apply(weights_init_normal_cyclegan)
+    return g_ab, g_ba, d_a, d_b

@@ -99,6 +99,11 @@ def _run_conv(conv, x, up=1, extra_pads=(0, 0, 0, 0), pad_mode=PAD_ZERO, act=ACT
     pad = int(conv.padding[0])
     if pad_mode == PAD_REFLECT and pad != 0:
         raise NotImplementedError("b200gan: reflection padding in front of a zero-padded conv")
+    if pad_mode == PAD_REFLECT and up == 1 and _tc_like(conv, 1):
+        # tensor-core path wants zero padding (TMA out-of-bounds fill): materialise the mirrored border once
+        # (cyclegan/models.py:27-28: ReflectionPad2d(1) -> Conv2d(256, 256, 3)) and run the conv un-padded
+        x = F.PadFn.apply(x, tuple(extra_pads), PAD_REFLECT)
+        extra_pads, pad_mode = (0, 0, 0, 0), PAD_ZERO
     pads = tuple(e + pad for e in extra_pads)
     spec = ConvSpec(stride=int(conv.stride[0]), pads=pads, pad_mode=pad_mode, up=up, transposed=transposed, act=act,
                     slope=slope, stats=stats, rtf_out=rtf_out, rtf_dz=rtf_dz)
@@ -242,7 +247,9 @@ class _ConvStep:
         self.rtf_dz = False
 
     def tc_like(self):
-        return self.pad_mode == PAD_ZERO and _tc_like(self.conv, self.up)
+        if self.pad_mode == PAD_REFLECT and self.up != 1:
+            return False
+        return _tc_like(self.conv, self.up)
 
 
 class _NormStep:
@@ -333,7 +340,10 @@ class Sequential(_T["Sequential"]):
         steps = self._plan()
         if all(isinstance(s, _LeafStep) for s in steps):
             return super().forward(x)
-        want_contiguous = x.is_contiguous()  # output memory format follows the input's
+        # Output memory format follows the input's -- the scripts .view() conv outputs only where they are small
+        # (dcgan.py:96: [N,128,4,4] -> [N,2048]); large maps stay NHWC so that U-Net / ResNet blocks chain and
+        # torch.cat (pix2pix/models.py:50) without a layout round trip per block.
+        want_contiguous = x.is_contiguous()
         stats = None
         for s in steps:
             if isinstance(s, _ConvStep):
@@ -353,7 +363,8 @@ class Sequential(_T["Sequential"]):
             else:
                 x = s.mod(x)
                 stats = None
-        if want_contiguous and torch.is_tensor(x) and x.dim() == 4 and not x.is_contiguous():
+        if (want_contiguous and torch.is_tensor(x) and x.dim() == 4 and not x.is_contiguous()
+                and x.shape[2] * x.shape[3] <= ops.Config.contiguous_hw_limit):
             x = F.ToContiguousFn.apply(x)
         return x
 

@@ -19,6 +19,9 @@ class Config:
     """Global switches. `algo`: 'auto' (tcgen05 where the geometry qualifies) or 'simt'."""
     algo = os.environ.get("B200GAN_ALGO", "auto")
     weight_cache = True
+    # a fused Sequential fed an NCHW-contiguous tensor returns an NCHW-contiguous tensor (what a script may .view,
+    # dcgan.py:96) only for feature maps of at most this many pixels; larger maps stay channels_last
+    contiguous_hw_limit = 64
 
 
 def _stream():

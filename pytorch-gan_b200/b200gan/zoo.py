@@ -124,3 +124,190 @@ class WGANGPDiscriminator(tnn.Module):
 
     def forward(self, img):
         return self.model(img.view(img.shape[0], -1))
+
+
+# ------------------------------------------------------------------------------------------------
+# Pix2Pix (BASELINE config 3): pix2pix/models.py:20-133
+# ------------------------------------------------------------------------------------------------
+def weights_init_normal_cyclegan(m):
+    """cyclegan/models.py:6-14: as above, plus conv biases set to 0."""
+    import torch
+    classname = m.__class__.__name__
+    if classname.find("Conv") != -1:
+        torch.nn.init.normal_(m.weight.data, 0.0, 0.02)
+        if hasattr(m, "bias") and m.bias is not None:
+            torch.nn.init.constant_(m.bias.data, 0.0)
+    elif classname.find("BatchNorm2d") != -1:
+        torch.nn.init.normal_(m.weight.data, 1.0, 0.02)
+        torch.nn.init.constant_(m.bias.data, 0.0)
+
+
+class UNetDown(tnn.Module):
+    """pix2pix/models.py:20-32."""
+
+    def __init__(self, in_size, out_size, normalize=True, dropout=0.0, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        layers = [nn.Conv2d(in_size, out_size, 4, 2, 1, bias=False)]
+        if normalize:
+            layers.append(nn.InstanceNorm2d(out_size))
+        layers.append(nn.LeakyReLU(0.2))
+        if dropout:
+            layers.append(nn.Dropout(dropout))
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class UNetUp(tnn.Module):
+    """pix2pix/models.py:35-52."""
+
+    def __init__(self, in_size, out_size, dropout=0.0, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        layers = [nn.ConvTranspose2d(in_size, out_size, 4, 2, 1, bias=False), nn.InstanceNorm2d(out_size),
+                  nn.ReLU(inplace=True)]
+        if dropout:
+            layers.append(nn.Dropout(dropout))
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x, skip_input):
+        import torch
+        return torch.cat((self.model(x), skip_input), 1)
+
+
+class GeneratorUNet(tnn.Module):
+    """pix2pix/models.py:55-101."""
+
+    def __init__(self, in_channels=3, out_channels=3, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        self.down1 = UNetDown(in_channels, 64, normalize=False, nn=nn)
+        self.down2 = UNetDown(64, 128, nn=nn)
+        self.down3 = UNetDown(128, 256, nn=nn)
+        self.down4 = UNetDown(256, 512, dropout=0.5, nn=nn)
+        self.down5 = UNetDown(512, 512, dropout=0.5, nn=nn)
+        self.down6 = UNetDown(512, 512, dropout=0.5, nn=nn)
+        self.down7 = UNetDown(512, 512, dropout=0.5, nn=nn)
+        self.down8 = UNetDown(512, 512, normalize=False, dropout=0.5, nn=nn)
+        self.up1 = UNetUp(512, 512, dropout=0.5, nn=nn)
+        self.up2 = UNetUp(1024, 512, dropout=0.5, nn=nn)
+        self.up3 = UNetUp(1024, 512, dropout=0.5, nn=nn)
+        self.up4 = UNetUp(1024, 512, dropout=0.5, nn=nn)
+        self.up5 = UNetUp(1024, 256, nn=nn)
+        self.up6 = UNetUp(512, 128, nn=nn)
+        self.up7 = UNetUp(256, 64, nn=nn)
+        self.final = nn.Sequential(nn.Upsample(scale_factor=2), nn.ZeroPad2d((1, 0, 1, 0)),
+                                   nn.Conv2d(128, out_channels, 4, padding=1), nn.Tanh())
+
+    def forward(self, x):
+        d1 = self.down1(x)
+        d2 = self.down2(d1)
+        d3 = self.down3(d2)
+        d4 = self.down4(d3)
+        d5 = self.down5(d4)
+        d6 = self.down6(d5)
+        d7 = self.down7(d6)
+        d8 = self.down8(d7)
+        u1 = self.up1(d8, d7)
+        u2 = self.up2(u1, d6)
+        u3 = self.up3(u2, d5)
+        u4 = self.up4(u3, d4)
+        u5 = self.up5(u4, d3)
+        u6 = self.up6(u5, d2)
+        u7 = self.up7(u6, d1)
+        return self.final(u7)
+
+
+class Pix2PixDiscriminator(tnn.Module):
+    """pix2pix/models.py:109-133 (PatchGAN on cat(A, B))."""
+
+    def __init__(self, in_channels=3, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+
+        def block(i, o, normalization=True):
+            layers = [nn.Conv2d(i, o, 4, stride=2, padding=1)]
+            if normalization:
+                layers.append(nn.InstanceNorm2d(o))
+            layers.append(nn.LeakyReLU(0.2, inplace=True))
+            return layers
+
+        self.model = nn.Sequential(*block(in_channels * 2, 64, normalization=False), *block(64, 128), *block(128, 256),
+                                   *block(256, 512), nn.ZeroPad2d((1, 0, 1, 0)),
+                                   nn.Conv2d(512, 1, 4, padding=1, bias=False))
+
+    def forward(self, img_A, img_B):
+        import torch
+        return self.model(torch.cat((img_A, img_B), 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# CycleGAN (BASELINE config 4): cyclegan/models.py:22-122
+# ------------------------------------------------------------------------------------------------
+class ResidualBlock(tnn.Module):
+    """cyclegan/models.py:22-37."""
+
+    def __init__(self, in_features, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        self.block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(in_features, in_features, 3),
+                                   nn.InstanceNorm2d(in_features), nn.ReLU(inplace=True), nn.ReflectionPad2d(1),
+                                   nn.Conv2d(in_features, in_features, 3), nn.InstanceNorm2d(in_features))
+
+    def forward(self, x):
+        return x + self.block(x)
+
+
+class GeneratorResNet(tnn.Module):
+    """cyclegan/models.py:40-87 (note: the first/last ReflectionPad2d take `channels` as pad, :49,:81)."""
+
+    def __init__(self, input_shape, num_residual_blocks, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        channels = input_shape[0]
+        out_features = 64
+        model = [nn.ReflectionPad2d(channels), nn.Conv2d(channels, out_features, 7), nn.InstanceNorm2d(out_features),
+                 nn.ReLU(inplace=True)]
+        in_features = out_features
+        for _ in range(2):
+            out_features *= 2
+            model += [nn.Conv2d(in_features, out_features, 3, stride=2, padding=1), nn.InstanceNorm2d(out_features),
+                      nn.ReLU(inplace=True)]
+            in_features = out_features
+        for _ in range(num_residual_blocks):
+            model += [ResidualBlock(out_features, nn=nn)]
+        for _ in range(2):
+            out_features //= 2
+            model += [nn.Upsample(scale_factor=2), nn.Conv2d(in_features, out_features, 3, stride=1, padding=1),
+                      nn.InstanceNorm2d(out_features), nn.ReLU(inplace=True)]
+            in_features = out_features
+        model += [nn.ReflectionPad2d(channels), nn.Conv2d(out_features, channels, 7), nn.Tanh()]
+        self.model = nn.Sequential(*model)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class CycleGANDiscriminator(tnn.Module):
+    """cyclegan/models.py:95-122."""
+
+    def __init__(self, input_shape, nn=None):
+        super().__init__()
+        nn = nn or namespace()
+        channels, height, width = input_shape
+        self.output_shape = (1, height // 2 ** 4, width // 2 ** 4)
+
+        def block(i, o, normalize=True):
+            layers = [nn.Conv2d(i, o, 4, stride=2, padding=1)]
+            if normalize:
+                layers.append(nn.InstanceNorm2d(o))
+            layers.append(nn.LeakyReLU(0.2, inplace=True))
+            return layers
+
+        self.model = nn.Sequential(*block(channels, 64, normalize=False), *block(64, 128), *block(128, 256),
+                                   *block(256, 512), nn.ZeroPad2d((1, 0, 1, 0)), nn.Conv2d(512, 1, 4, padding=1))
+
+    def forward(self, img):
+        return self.model(img)

@@ -106,6 +106,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *s
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// TMA reduce-store: global[box] += smem[box] (fp32 add performed at L2), tile mode, bulk-group completion
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, const void *src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -12,9 +12,10 @@
 // The upsample-folded convolution (dcgan.py:54-55,58-59) contributes 16 (phase, tap) jobs that read dy
 // through the phase view {2K, Q/2, 2, P/2, N}; a second kernel folds them back into the 3x3 filter.
 //
-// Parallelisation: grid = (pixel splits, jobs, M-tiles x N-tiles).  Every CTA accumulates its pixel
-// range in TMEM and stores a partial tile; wgrad_reduce_kernel sums the partials in a fixed order
-// (deterministic, no atomics) while converting to the parameter layout [K][C][R][S].
+// Parallelisation: grid = (pixel splits, jobs, M-tiles x N-tiles).  Every CTA accumulates its pixel range in
+// TMEM, stages the tile in shared memory and adds it into the job's [M'][N'] matrix with a TMA reduce-store
+// (cp.reduce.async.bulk.tensor ... .add: the fp32 additions happen at L2); wgrad_reduce_kernel then folds the
+// jobs into the parameter layout [K][C][R][S].
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -42,7 +43,7 @@ struct WgParams {
   int32_t mtiles, ntiles;         // tiles of the (M', N') output
   int32_t ldn;                    // N' total (row length of a partial matrix)
   int32_t mtotal;                 // M' total
-  float *partial;                 // [split][job][M'][N']
+  float *partial;                 // [job][M'][N'], zeroed by the host; splits accumulate with TMA reduce-add
   uint32_t lbo, sbo;              // UMMA descriptor byte offsets (chunk stride, 8-row group stride)
 };
 
@@ -172,10 +173,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     fence_proxy_async();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x == 64) {
-      const int row0 = (split * p.njobs + job) * p.mtotal + mt * 128;
+      // all pixel splits of a job accumulate into the same [job][M'][N'] tile: TMA reduce-add (fp32 add at L2)
+      const int row0 = job * p.mtotal + mt * 128;
+      if (iters > 0) {
 #pragma unroll 1
-      for (int c = 0; c < NB; c += 32) tma_store_2d(&tmP, smem + (c >> 5) * 16384, nt * NB + c, row0);
-      tma_store_commit_and_wait_read();
+        for (int c = 0; c < NB; c += 32) tma_reduce_add_2d(&tmP, smem + (c >> 5) * 16384, nt * NB + c, row0);
+        tma_store_commit_and_wait_read();
+      }
     }
   }
   tc_fence_before();
@@ -283,7 +287,7 @@ int tc_wgrad_supported(const b200gan_conv_geom *g) {
 size_t tc_wgrad_workspace_floats(const b200gan_conv_geom *g) {
   WgPlan pl;
   if (!wg_plan(g, pl)) return 0;
-  return (size_t)pl.nsplits * pl.njobs * pl.mtotal * pl.ldn;
+  return (size_t)pl.njobs * pl.mtotal * pl.ldn;
 }
 
 template <int NB, int STAGES>
@@ -357,16 +361,17 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   }
   CUtensorMap tmP;
   {
-    uint64_t dims[2] = {(uint64_t)pl.ldn, (uint64_t)pl.nsplits * pl.njobs * pl.mtotal};
+    uint64_t dims[2] = {(uint64_t)pl.ldn, (uint64_t)pl.njobs * pl.mtotal};
     uint64_t strides[1] = {(uint64_t)pl.ldn * 4};
     uint32_t pbox[2] = {32, 128};
     if (int e = make_tmap_f32(&tmP, ws, 2, dims, strides, pbox)) return e;
   }
+  B2_CUDA(cudaMemsetAsync(ws, 0, (size_t)pl.njobs * pl.mtotal * pl.ldn * sizeof(float), st));
   dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
   int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, tmP, p, grid, st) : launch_wg<64, 4>(tmX, tmY, tmP, p, grid, st);
   if (rc) return rc;
   WgReduceP rp;
-  rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.nsplits = pl.nsplits; rp.njobs = pl.njobs;
+  rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.nsplits = 1; rp.njobs = pl.njobs;
   rp.x_is_a = pl.x_is_a; rp.up2 = up2 ? 1 : 0; rp.mtotal = pl.mtotal; rp.ldn = pl.ldn;
   int64_t total = (int64_t)g->K * g->C * g->R * g->S;
   unsigned blocks = (unsigned)(ceil_div64(total, 256) > 2368 ? 2368 : ceil_div64(total, 256));

@@ -230,3 +230,16 @@ def test_launcher_builds_dcgan_with_drop_in_modules():
     assert isinstance(gen.conv_blocks, bnn.Sequential) and isinstance(gen.conv_blocks[2], bnn.Conv2d)
     for k, v in ref.state_dict().items():   # same init draws as the stock run of the same script
         assert torch.equal(gen.state_dict()[k], v), k
+
+
+def test_pix2pix_and_cyclegan_oracle_against_reference_golden(golden_dir):
+    fix = torch.load(os.path.join(golden_dir, "cyclegan_64_b2.pt"), weights_only=False)
+    shape = (3, fix["size"], fix["size"])
+    g_ab, g_ba, d_a, d_b = ref_models.build_cyclegan(shape, fix["blocks"], fix["seed"])
+    real_a = ref_models.synthetic_images(fix["batch"], 3, fix["size"], fix["size"], seed=fix["seed"] + 1)
+    with torch.no_grad():
+        fake_b = g_ab(real_a)
+    assert rel_err(fake_b[..., ::4, ::4], fix["fake_b"]) < 1e-6
+    fixp = torch.load(os.path.join(golden_dir, "pix2pix_256_b1.pt"), weights_only=False)
+    _, d = ref_models.build_pix2pix(fixp["seed"])
+    assert sorted(d.state_dict().keys()) == sorted(k for k in fixp["d_grad_norms"].keys())

@@ -1,0 +1,124 @@
+"""GPU parity for BASELINE configs 3 and 4: the pix2pix U-Net / PatchGAN and the CycleGAN ResNet generator /
+discriminator built from the drop-in modules, against (a) golden vectors produced by the reference's own
+models.py on CPU (oracle/make_golden.py) and (b) the oracle restatement on stock torch fp32 on this GPU."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_models
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _grad_norm_check(model, ref_norms, tol, what):
+    for k, p in model.named_parameters():
+        rn = ref_norms[k]
+        if rn < 1e-6:   # conv bias in front of InstanceNorm: exactly-zero gradient
+            continue
+        assert abs(p.grad.double().norm().item() - rn) < tol * rn, f"{what} {k}"
+
+
+def test_pix2pix_against_reference_golden(golden_dir):
+    from b200gan import zoo
+    fix = torch.load(os.path.join(golden_dir, "pix2pix_256_b1.pt"), weights_only=False)
+    g_cpu, d_cpu = ref_models.build_pix2pix(fix["seed"])
+    g, d = zoo.GeneratorUNet(), zoo.Pix2PixDiscriminator()
+    g.load_state_dict(g_cpu.state_dict())
+    d.load_state_dict(d_cpu.state_dict())
+    g, d = g.cuda().eval(), d.cuda().train()
+    size, n = fix["size"], fix["batch"]
+    real_a = ref_models.synthetic_images(n, 3, size, size, seed=fix["seed"] + 1).cuda()
+    real_b = ref_models.synthetic_images(n, 3, size, size, seed=fix["seed"] + 2).cuda()
+    fake_b = g(real_a)
+    assert fake_b.shape == (n, 3, size, size)
+    assert rel_err(fake_b[..., ::8, ::8], fix["fake_b"]) < TOL
+    pred = d(fake_b, real_a)
+    assert pred.shape == fix["pred"].shape
+    assert rel_err(pred, fix["pred"]) < 2 * TOL
+    loss = torch.nn.MSELoss()(pred, torch.ones_like(pred)) + 100 * torch.nn.L1Loss()(fake_b, real_b)
+    assert abs(loss.item() - fix["loss"].item()) < TOL * abs(fix["loss"].item())
+    loss.backward()
+    _grad_norm_check(g, fix["g_grad_norms"], 1e-2, "pix2pix G")
+    _grad_norm_check(d, fix["d_grad_norms"], 1e-2, "pix2pix D")
+
+
+def test_pix2pix_channels_last_chain_and_dropout_training_mode():
+    """Training-mode forward (Dropout active) keeps every block channels_last (no layout round trips) and
+    produces the statistics of dropout: finite outputs, right shapes, backward runs."""
+    from b200gan import zoo
+    torch.manual_seed(0)
+    g = zoo.GeneratorUNet().cuda().train()
+    x = torch.randn(2, 3, 256, 256, device="cuda")
+    d1 = g.down1(x)
+    assert d1.is_contiguous(memory_format=torch.channels_last) and not d1.is_contiguous()
+    y = g(x)
+    assert y.shape == (2, 3, 256, 256) and bool(torch.isfinite(y).all())
+    y.mean().backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in g.parameters())
+
+
+def test_cyclegan_against_reference_golden(golden_dir):
+    from b200gan import zoo
+    fix = torch.load(os.path.join(golden_dir, "cyclegan_64_b2.pt"), weights_only=False)
+    size, n, blocks = fix["size"], fix["batch"], fix["blocks"]
+    shape = (3, size, size)
+    nets_cpu = ref_models.build_cyclegan(shape, blocks, fix["seed"])
+    nets = [zoo.GeneratorResNet(shape, blocks), zoo.GeneratorResNet(shape, blocks), zoo.CycleGANDiscriminator(shape),
+            zoo.CycleGANDiscriminator(shape)]
+    for m, r in zip(nets, nets_cpu):
+        m.load_state_dict(r.state_dict())
+        m.cuda().train()
+    g_ab, g_ba, d_a, d_b = nets
+    real_a = ref_models.synthetic_images(n, 3, size, size, seed=fix["seed"] + 1).cuda()
+    real_b = ref_models.synthetic_images(n, 3, size, size, seed=fix["seed"] + 2).cuda()
+    mse, l1 = torch.nn.MSELoss(), torch.nn.L1Loss()
+    valid = torch.ones(n, *d_a.output_shape, device="cuda")
+    loss_id = (l1(g_ba(real_a), real_a) + l1(g_ab(real_b), real_b)) / 2
+    fake_b, fake_a = g_ab(real_a), g_ba(real_b)
+    assert rel_err(fake_b[..., ::4, ::4], fix["fake_b"]) < TOL
+    assert rel_err(fake_a[..., ::4, ::4], fix["fake_a"]) < TOL
+    loss_gan = (mse(d_b(fake_b), valid) + mse(d_a(fake_a), valid)) / 2
+    loss_cyc = (l1(g_ba(fake_b), real_a) + l1(g_ab(fake_a), real_b)) / 2
+    for ours, ref in zip((loss_id, loss_gan, loss_cyc), fix["parts"]):
+        assert abs(ours.item() - ref) < TOL * abs(ref)
+    loss_g = loss_gan + 10.0 * loss_cyc + 5.0 * loss_id
+    assert abs(loss_g.item() - fix["loss_g"].item()) < TOL * abs(fix["loss_g"].item())
+    loss_g.backward()
+    _grad_norm_check(g_ab, fix["g_ab_grad_norms"], 2e-2, "cyclegan G_AB")
+    _grad_norm_check(g_ba, fix["g_ba_grad_norms"], 2e-2, "cyclegan G_BA")
+
+
+@pytest.mark.parametrize("which", ["pix2pix_d", "cyclegan_g"])
+def test_models_vs_stock_torch_on_gpu(which):
+    """Same weights, same inputs, stock torch fp32 on this GPU: outputs and all parameter gradients."""
+    from b200gan import zoo
+    if which == "pix2pix_d":
+        _, ref = ref_models.build_pix2pix(1)
+        ours = zoo.Pix2PixDiscriminator()
+        args = [torch.randn(4, 3, 128, 128, device="cuda"), torch.randn(4, 3, 128, 128, device="cuda")]
+    else:
+        ref = ref_models.build_cyclegan((3, 64, 64), 3, 1)[0]
+        ours = zoo.GeneratorResNet((3, 64, 64), 3)
+        args = [torch.randn(2, 3, 64, 64, device="cuda")]
+    ours.load_state_dict(ref.state_dict())
+    ref, ours = ref.cuda().train(), ours.cuda().train()
+    yr = ref(*args)
+    yo = ours(*args)
+    assert rel_err(yo, yr) < TOL
+    gy = torch.randn_like(yr)
+    yr.backward(gy)
+    yo.backward(gy)
+    for (k, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+        if pr.grad.double().norm().item() < 1e-6 or k.endswith("bias"):
+            continue
+        assert rel_err(po.grad, pr.grad) < 1e-2, k

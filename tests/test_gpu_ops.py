@@ -136,7 +136,7 @@ def test_upsample_conv_folded(cin, cout, h, w, n):
     xr = x.clone().requires_grad_(True)
     xo = x.clone().requires_grad_(True)
     yr, yo = ref(xr), ours(xo)
-    assert yo.shape == yr.shape and yo.is_contiguous()
+    assert yo.shape == yr.shape
     assert rel_err(yo, yr) < TOL
     gy = torch.randn_like(yr)
     yr.backward(gy)
