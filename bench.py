@@ -167,6 +167,15 @@ def time_conv_kernel(torch, iters=20):
             "bytes": bytes_alg}
 
 
+def _finish(world):
+    """Leave without tearing NCCL down: destroy_process_group() can block while CUDA graphs that captured
+    collectives are still alive, and the measurement is already printed."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -264,8 +273,7 @@ def run_ours(args):
     ms, ms_e2e = t.tolist()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     hbm_peak, bf16_peak, peak_src = measured_peaks()
@@ -306,9 +314,8 @@ def run_ours(args):
         "step_tensor_fraction_reference_form": GFLOP_PER_STEP_REFERENCE_FORM / step_ms / tf32_peak,
         "final_losses": {"g": losses[0], "d": losses[1]},
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _finish(world)
 
 
 if __name__ == "__main__":

@@ -188,9 +188,10 @@ int b200gan_upsample2x_fwd(const float *x, float *y, int32_t N, int32_t H, int32
 int b200gan_upsample2x_bwd(const float *dy, float *dx, int32_t N, int32_t H, int32_t W, int32_t C,
                            void *stream);
 /* Constant-zero or reflection padding and its gradient (crop / fold), NHWC. */
+/* round_tf32: store RN-rounded TF32 values (the padded copy feeds a tcgen05 conv) */
 int b200gan_pad2d_fwd(const float *x, float *y, int32_t N, int32_t H, int32_t W, int32_t C,
                       int32_t pad_t, int32_t pad_l, int32_t pad_b, int32_t pad_r, int32_t mode,
-                      void *stream);
+                      int32_t round_tf32, void *stream);
 int b200gan_pad2d_bwd(const float *dy, float *dx, int32_t N, int32_t H, int32_t W, int32_t C,
                       int32_t pad_t, int32_t pad_l, int32_t pad_b, int32_t pad_r, int32_t mode,
                       void *stream);

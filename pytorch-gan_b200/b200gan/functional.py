@@ -213,13 +213,13 @@ class UpsampleFn(torch.autograd.Function):
 
 class PadFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, pads, mode):
+    def forward(ctx, x, pads, mode, round_tf32=False):
         ctx.pads, ctx.mode = pads, mode
-        return ops.pad2d(_as_cl(x), pads, mode)
+        return ops.pad2d(_as_cl(x), pads, mode, round_tf32)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.pad2d_bwd(_as_cl(dy), ctx.pads, ctx.mode), None, None
+        return ops.pad2d_bwd(_as_cl(dy), ctx.pads, ctx.mode), None, None, None
 
 
 class ActFn(torch.autograd.Function):

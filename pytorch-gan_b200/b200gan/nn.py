@@ -102,7 +102,7 @@ def _run_conv(conv, x, up=1, extra_pads=(0, 0, 0, 0), pad_mode=PAD_ZERO, act=ACT
     if pad_mode == PAD_REFLECT and up == 1 and _tc_like(conv, 1):
         # tensor-core path wants zero padding (TMA out-of-bounds fill): materialise the mirrored border once
         # (cyclegan/models.py:27-28: ReflectionPad2d(1) -> Conv2d(256, 256, 3)) and run the conv un-padded
-        x = F.PadFn.apply(x, tuple(extra_pads), PAD_REFLECT)
+        x = F.PadFn.apply(x, tuple(extra_pads), PAD_REFLECT, True)  # RN-round: operands of a TF32 MMA
         extra_pads, pad_mode = (0, 0, 0, 0), PAD_ZERO
     pads = tuple(e + pad for e in extra_pads)
     spec = ConvSpec(stride=int(conv.stride[0]), pads=pads, pad_mode=pad_mode, up=up, transposed=transposed, act=act,

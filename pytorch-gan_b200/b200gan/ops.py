@@ -232,12 +232,12 @@ def upsample2x_bwd(dy):
     return dx
 
 
-def pad2d(x, pads, mode):
+def pad2d(x, pads, mode, round_tf32=False):
     n, c, h, w = x.shape
     t, l, b, r = pads
     y = empty_cl(n, c, h + t + b, w + l + r, x.device)
-    _lib.check(_lib.load().b200gan_pad2d_fwd(x.data_ptr(), y.data_ptr(), n, h, w, c, t, l, b, r, mode, _stream()),
-               "pad2d_fwd")
+    _lib.check(_lib.load().b200gan_pad2d_fwd(x.data_ptr(), y.data_ptr(), n, h, w, c, t, l, b, r, mode, int(round_tf32),
+                                             _stream()), "pad2d_fwd")
     return y
 
 

@@ -143,10 +143,14 @@ conv_gather_gemm_kernel(GatherP g, EpiP ep, const float *__restrict__ x,
       int n = n0 + b_n;
       float v = 0.f;
       if (k < Ktot && n < K) {
-        int c = k % g.C;
-        int t = k / g.C;
-        int s = s0 + cls * (t % Sc), r = r0 + cls * (t / Sc);
-        v = __ldg(wp + ((int64_t)(r * g.S + s) * g.C + c) * K + n);
+        if (cls == 1) {
+          v = __ldg(wp + (int64_t)k * K + n);
+        } else {
+          int c = k % g.C;
+          int t = k / g.C;
+          int s = s0 + cls * (t % Sc), r = r0 + cls * (t / Sc);
+          v = __ldg(wp + ((int64_t)(r * g.S + s) * g.C + c) * K + n);
+        }
       }
       Bs[b_k + 4 * i][b_n] = v;
     }

@@ -78,7 +78,7 @@ __global__ void upsample2x_bwd_kernel(const float *__restrict__ dy, float *__res
 
 // ---- padding ------------------------------------------------------------------------------------
 __global__ void pad2d_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t total, int H,
-                                 int W, int C, int Ho, int Wo, int pad_t, int pad_l, int mode) {
+                                 int W, int C, int Ho, int Wo, int pad_t, int pad_l, int mode, int rtf) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -96,7 +96,7 @@ __global__ void pad2d_fwd_kernel(const float *__restrict__ x, float *__restrict_
     } else if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
       v = __ldg(x + (((int64_t)n * H + ih) * W + iw) * C + c);
     }
-    y[i] = v;
+    y[i] = rtf ? round_tf32(v) : v;
   }
 }
 // gradient: zero pad -> crop; reflect -> each input pixel sums the (<= 4) padded pixels that mirror
@@ -240,7 +240,7 @@ extern "C" int b200gan_upsample2x_bwd(const float *dy, float *dx, int32_t N, int
 
 extern "C" int b200gan_pad2d_fwd(const float *x, float *y, int32_t N, int32_t H, int32_t W, int32_t C,
                                  int32_t pad_t, int32_t pad_l, int32_t pad_b, int32_t pad_r, int32_t mode,
-                                 void *stream) {
+                                 int32_t round_tf32_, void *stream) {
   B2_CHECK_ARG(x && y, "pad2d_fwd: null pointer");
   B2_CHECK_ARG(mode != B200GAN_PAD_REFLECT || (pad_t < H && pad_b < H && pad_l < W && pad_r < W),
                "pad2d_fwd: reflection pad must be smaller than the input");
@@ -248,7 +248,7 @@ extern "C" int b200gan_pad2d_fwd(const float *x, float *y, int32_t N, int32_t H,
   int64_t total = (int64_t)N * Ho * Wo * C;
   if (total == 0) return B200GAN_OK;
   pad2d_fwd_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, total, H, W, C, Ho, Wo, pad_t,
-                                                                         pad_l, mode);
+                                                                         pad_l, mode, round_tf32_);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
