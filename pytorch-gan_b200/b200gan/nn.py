@@ -76,9 +76,12 @@ def _conv_ok(m):
 
 def _tc_like(conv, up):
     """Static mirror of tc_supported() used to decide where TF32 rounding of operands pays."""
-    if ops.Config.algo == "simt" or isinstance(conv, _T["ConvTranspose2d"]):
+    if ops.Config.algo == "simt":
         return False
-    return conv.stride[0] == 1 and conv.in_channels % 32 == 0 and conv.out_channels % 64 == 0
+    if up == 2:
+        return (not isinstance(conv, _T["ConvTranspose2d"]) and conv.stride[0] == 1 and conv.in_channels % 32 == 0
+                and conv.out_channels % 64 == 0)
+    return conv.stride[0] in (1, 2) and conv.in_channels % 32 == 0 and conv.out_channels % 32 == 0
 
 
 def _dropout2d_scale(x_shape, p, device):

@@ -81,7 +81,8 @@ constexpr int TC_THREADS = 192;
 struct TcTap {
   int16_t dc;  // channel base offset in the A view (selects the w-parity half of a phase view)
   int8_t dw, da, dh;
-  int8_t pad_[3];
+  int8_t bt;   // row block of this tap in the packed weight matrix (B rows = bt * Kout + ...)
+  int8_t pad_[2];
 };
 
 struct TcParams {
@@ -184,7 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (it < 16) TC_TRACE(2 + it);
         mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
         tma_load_5d(sa, &tmA, &full[stage], tp.dc + kc * TC_BK, w0 + tp.dw, tp.da, h0 + tp.dh, n0);
-        tma_load_2d(sb, &tmB, &full[stage], kc * TC_BK, (tap0 + tap) * p.kout_total + ntile * BN);
+        tma_load_2d(sb, &tmB, &full[stage], kc * TC_BK, tp.bt * p.kout_total + ntile * BN);
         if (++kc == p.kchunks) {
           kc = 0;
           ++tap;
@@ -360,32 +361,55 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUten
 int tc_wgrad_supported(const b200gan_conv_geom *g);  // wgrad_tc.cu
 
 // Which passes of which geometries the tcgen05 path takes.
+//   gather form  (out[p] = sum_t in[stride*p + off_t] B_t): Conv2d fprop, ConvTranspose2d dgrad
+//   scatter form (out[h] = sum_{t | stride divides h+pad-t} in[(h+pad-t)/stride] B_t): Conv2d dgrad, ConvTranspose2d fprop
+// stride 2 is handled with parity views: the gathered tensor {2C, W/2, 2, H/2, N} for the gather form, the
+// produced tensor (four output phases with their own tap subsets) for the scatter form.
+static bool tc_is_gather(const b200gan_conv_geom *g, int pass) { return (pass == 0) != (g->transposed != 0); }
+
 int tc_supported(const b200gan_conv_geom *g, int pass) {
-  if (g->transposed || g->stride != 1 || g->pad_mode != B200GAN_PAD_ZERO) return 0;
-  if (g->N < 1) return 0;
+  if (g->pad_mode != B200GAN_PAD_ZERO || g->N < 1) return 0;
   if (pass == 2) return tc_wgrad_supported(g);  // weight gradient: wgrad_tc.cu
+  if (g->stride != 1 && g->stride != 2) return 0;
   const int cin = pass == 0 ? g->C : g->K;   // contraction channels
   const int cout = pass == 0 ? g->K : g->C;  // produced channels
-  if (cin % 32 != 0 || cout % 64 != 0) return 0;
-  if (g->R * g->S > 49) return 0;
+  if (cin % 32 != 0 || cout % 32 != 0 || 2 * cin > 32767) return 0;
+  if (g->R * g->S > 49 || g->R > 15 || g->S > 15 || g->pad_t > 15 || g->pad_l > 15) return 0;
   if (g->up == 2) {
+    if (g->transposed || g->stride != 1) return 0;
     if (!(g->R == 3 && g->S == 3 && g->pad_t == 1 && g->pad_l == 1 && g->pad_b == 1 && g->pad_r == 1)) return 0;
-    if (2 * cin > 32767) return 0;
+    return cout % 64 == 0;
   }
-  if (g->pad_t > 100 || g->pad_l > 100 || g->R > 100 || g->S > 100) return 0;
+  if (g->stride == 2) {
+    // the full-resolution side (Conv2d input / ConvTranspose2d output) is the one seen through a parity view
+    const int Hf = g->transposed ? g->P : g->H, Wf = g->transposed ? g->Q : g->W;
+    if ((Hf & 1) || (Wf & 1)) return 0;
+    if (!tc_is_gather(g, pass)) {  // scatter form: 4 phases, each at most 16 taps in total budget
+      int taps = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          int nr = 0, ns = 0;
+          for (int r = 0; r < g->R; ++r) nr += ((a + g->pad_t - r) % 2 == 0);
+          for (int s2 = 0; s2 < g->S; ++s2) ns += ((b + g->pad_l - s2) % 2 == 0);
+          taps += nr * ns;
+        }
+      if (taps > TC_MAX_TAPS) return 0;
+    }
+  }
   return 1;
 }
 
 // Shared by fprop and dgrad.
 //  in      : contracted activation tensor [N][Hi][Wi][Cc] (x for fprop, dy for dgrad)
-//  phase_in: 1 -> `in` is addressed through the phase view {2Cc, Wi/2, 2, Hi/2, N} (dgrad of UP2)
+//  phase_in: 1 -> `in` is addressed through the parity view {2Cc, Wi/2, 2, Hi/2, N} (dgrad of UP2; stride-2 gathers)
+//  btaps   : number of tap blocks in the packed weight matrix (rows = btaps * Kout)
 //  out     : N x Ho x Wo pixels per phase.  phase_out: 1 -> y is the full-resolution tensor [N][2Ho][2Wo][ldk]
 //            addressed through the phase view {2*ldk, Wo, 2, Ho, N}; phase z writes (out_dc[z], out_da[z]).
 static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in, const float *packedB, int Kout,
-                  int nphase, const int *tap_begin, const TcTap *taps, int Ho, int Wo, bool phase_out,
+                  int btaps, int nphase, const int *tap_begin, const TcTap *taps, int Ho, int Wo, bool phase_out,
                   const int *out_dc, const int *out_da, int ldk, const b200gan_epilogue *ep, float *y,
                   cudaStream_t st) {
-  const int BN = (Kout % 128 == 0) ? 128 : 64;
+  const int BN = (Kout % 128 == 0) ? 128 : (Kout % 64 == 0 ? 64 : 32);
   TcParams p;
   memset(&p, 0, sizeof(p));
   const int total_taps = tap_begin[nphase];
@@ -458,84 +482,147 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
     if (int e = make_tmap_f32(&tmA, in, 5, dims, strides, box)) return e;
   }
   {
-    uint64_t dims[2] = {(uint64_t)Cc, (uint64_t)total_taps * Kout};
+    uint64_t dims[2] = {(uint64_t)Cc, (uint64_t)btaps * Kout};
     uint64_t strides[1] = {(uint64_t)Cc * 4};
     uint32_t box[2] = {TC_BK, (uint32_t)BN};
     if (int e = make_tmap_f32(&tmB, packedB, 2, dims, strides, box)) return e;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)nphase);
   if (BN == 128) return launch_tc<128, 3>(tmA, tmB, tmY, p, grid, st);
-  return launch_tc<64, 4>(tmA, tmB, tmY, p, grid, st);
+  if (BN == 64) return launch_tc<64, 4>(tmA, tmB, tmY, p, grid, st);
+  return launch_tc<32, 4>(tmA, tmB, tmY, p, grid, st);
 }
 
-int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
-             cudaStream_t st) {
+static inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+// gather form.  in: [N][Hi][Wi][Cc]; out: [N][Po][Qo][Kout]; B: [R*S][Kout][Cc]
+static int tc_gather(const float *in, int N, int Hi, int Wi, int Cc, int R, int S, int stride, int pad_t, int pad_l,
+                     const float *packedB, int Kout, int Po, int Qo, const b200gan_epilogue *ep, float *out,
+                     cudaStream_t st) {
   TcTap taps[TC_MAX_TAPS];
   memset(taps, 0, sizeof(taps));
   int tap_begin[5] = {0, 0, 0, 0, 0};
   int out_dc[4] = {0, 0, 0, 0}, out_da[4] = {0, 0, 0, 0};
+  int nt = 0;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      TcTap &t = taps[nt];
+      const int eh = r - pad_t, ew = s - pad_l;
+      if (stride == 1) {
+        t.dc = 0; t.dw = (int8_t)ew; t.da = 0; t.dh = (int8_t)eh;
+      } else {  // in[2p + eh] = parity view [p + floor(eh/2)][eh mod 2]
+        t.dh = (int8_t)floordiv2(eh); t.da = (int8_t)(eh & 1);
+        t.dw = (int8_t)floordiv2(ew); t.dc = (int16_t)((ew & 1) * Cc);
+      }
+      t.bt = (int8_t)nt;
+      ++nt;
+    }
+  tap_begin[1] = nt;
+  return run_tc(in, N, Hi, Wi, Cc, stride == 2, packedB, Kout, R * S, 1, tap_begin, taps, Po, Qo, false, out_dc, out_da,
+                Kout, ep, out, st);
+}
+
+// scatter form.  in: [N][Pi][Qi][Cc]; out: [N][Ho][Wo][Kout] (full resolution); B: [R*S][Kout][Cc]
+static int tc_scatter(const float *in, int N, int Pi, int Qi, int Cc, int R, int S, int stride, int pad_t, int pad_l,
+                      const float *packedB, int Kout, int Ho, int Wo, const b200gan_epilogue *ep, float *out,
+                      cudaStream_t st) {
+  TcTap taps[TC_MAX_TAPS];
+  memset(taps, 0, sizeof(taps));
+  int tap_begin[5] = {0, 0, 0, 0, 0};
+  int out_dc[4] = {0, 0, 0, 0}, out_da[4] = {0, 0, 0, 0};
+  if (stride == 1) {
+    int nt = 0;
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s) {
+        TcTap &t = taps[nt];
+        t.dc = 0; t.dw = (int8_t)(pad_l - s); t.da = 0; t.dh = (int8_t)(pad_t - r); t.bt = (int8_t)nt;
+        ++nt;
+      }
+    tap_begin[1] = nt;
+    return run_tc(in, N, Pi, Qi, Cc, false, packedB, Kout, R * S, 1, tap_begin, taps, Ho, Wo, false, out_dc, out_da, Kout,
+                  ep, out, st);
+  }
+  int nt = 0;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int a = ph >> 1, b = ph & 1;
+    tap_begin[ph] = nt;
+    for (int r = 0; r < R; ++r) {
+      if ((a + pad_t - r) % 2 != 0) continue;
+      for (int s = 0; s < S; ++s) {
+        if ((b + pad_l - s) % 2 != 0) continue;
+        TcTap &t = taps[nt++];
+        t.dc = 0; t.da = 0;
+        t.dh = (int8_t)((a + pad_t - r) / 2);  // exact: numerator is even
+        t.dw = (int8_t)((b + pad_l - s) / 2);
+        t.bt = (int8_t)(r * S + s);
+      }
+    }
+    out_dc[ph] = b * Kout;
+    out_da[ph] = a;
+  }
+  tap_begin[4] = nt;
+  return run_tc(in, N, Pi, Qi, Cc, false, packedB, Kout, R * S, 4, tap_begin, taps, Ho / 2, Wo / 2, true, out_dc, out_da,
+                Kout, ep, out, st);
+}
+
+int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
+             cudaStream_t st) {
   b200gan_epilogue e2;
   if (ep) {
     e2 = *ep;
     // per-sample (InstanceNorm) sums can only be fused when a tile never spans two images
     if (e2.stats && e2.stats_per_sample) B2_UNSUPPORTED("tcgen05 fprop: per-sample statistics are not fused");
   }
+  const b200gan_epilogue *e = ep ? &e2 : nullptr;
   if (g->up == 2) {
     // phase (a,b): out[2i+a][2j+b] = sum_{dr,ds} x[i+a-1+dr][j+b-1+ds] * Wf[a][b][dr][ds]
+    TcTap taps[TC_MAX_TAPS];
+    memset(taps, 0, sizeof(taps));
+    int tap_begin[5] = {0, 4, 8, 12, 16};
+    int out_dc[4], out_da[4];
     for (int ph = 0; ph < 4; ++ph) {
       int a = ph >> 1, b = ph & 1;
-      tap_begin[ph] = ph * 4;
       for (int tp = 0; tp < 4; ++tp) {
         int dr = tp >> 1, ds = tp & 1;
         TcTap &t = taps[ph * 4 + tp];
-        t.dc = 0; t.dw = (int8_t)(b - 1 + ds); t.da = 0; t.dh = (int8_t)(a - 1 + dr);
+        t.dc = 0; t.dw = (int8_t)(b - 1 + ds); t.da = 0; t.dh = (int8_t)(a - 1 + dr); t.bt = (int8_t)(ph * 4 + tp);
       }
       out_dc[ph] = b * g->K;
       out_da[ph] = a;
     }
-    tap_begin[4] = 16;
-    return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 4, tap_begin, taps, g->H, g->W, true, out_dc, out_da,
-                  g->K, ep ? &e2 : nullptr, y, st);
+    return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 16, 4, tap_begin, taps, g->H, g->W, true, out_dc, out_da,
+                  g->K, e, y, st);
   }
-  int nt = 0;
-  for (int r = 0; r < g->R; ++r)
-    for (int s = 0; s < g->S; ++s) {
-      TcTap &t = taps[nt++];
-      t.dc = 0; t.dw = (int8_t)(s - g->pad_l); t.da = 0; t.dh = (int8_t)(r - g->pad_t);
-    }
-  tap_begin[1] = nt;
-  return run_tc(x, g->N, g->H, g->W, g->C, false, packed, g->K, 1, tap_begin, taps, g->P, g->Q, false, out_dc, out_da,
-                g->K, ep ? &e2 : nullptr, y, st);
+  if (g->transposed)  // ConvTranspose2d forward: scatter x into the (stride x larger) output
+    return tc_scatter(x, g->N, g->H, g->W, g->C, g->R, g->S, g->stride, g->pad_t, g->pad_l, packed, g->K, g->P, g->Q, e, y,
+                      st);
+  return tc_gather(x, g->N, g->H, g->W, g->C, g->R, g->S, g->stride, g->pad_t, g->pad_l, packed, g->K, g->P, g->Q, e, y, st);
 }
 
 int tc_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, float *dx, cudaStream_t st) {
-  TcTap taps[TC_MAX_TAPS];
-  memset(taps, 0, sizeof(taps));
-  int tap_begin[5] = {0, 0, 0, 0, 0};
-  int out_dc[4] = {0, 0, 0, 0}, out_da[4] = {0, 0, 0, 0};
   if (g->up == 2) {
     // dx[i][j] = sum_{a,b,dr,ds} dy[2(i-(a-1+dr))+a][2(j-(b-1+ds))+b] * Wf[a][b][dr][ds]^T
+    TcTap taps[TC_MAX_TAPS];
+    memset(taps, 0, sizeof(taps));
+    int tap_begin[5] = {0, 16, 16, 16, 16};
+    int out_dc[4] = {0, 0, 0, 0}, out_da[4] = {0, 0, 0, 0};
     for (int ph = 0; ph < 4; ++ph) {
       int a = ph >> 1, b = ph & 1;
       for (int tp = 0; tp < 4; ++tp) {
         int dr = tp >> 1, ds = tp & 1;
         TcTap &t = taps[ph * 4 + tp];
         t.dc = (int16_t)(b * g->K); t.dw = (int8_t)(-(b - 1 + ds)); t.da = (int8_t)a; t.dh = (int8_t)(-(a - 1 + dr));
+        t.bt = (int8_t)(ph * 4 + tp);
       }
     }
-    tap_begin[1] = 16;
-    return run_tc(dy, g->N, g->P, g->Q, g->K, true, packed, g->C, 1, tap_begin, taps, g->H, g->W, false, out_dc, out_da,
+    return run_tc(dy, g->N, g->P, g->Q, g->K, true, packed, g->C, 16, 1, tap_begin, taps, g->H, g->W, false, out_dc, out_da,
                   g->C, nullptr, dx, st);
   }
-  int nt = 0;
-  for (int r = 0; r < g->R; ++r)
-    for (int s = 0; s < g->S; ++s) {
-      TcTap &t = taps[nt++];
-      t.dc = 0; t.dw = (int8_t)(g->pad_l - s); t.da = 0; t.dh = (int8_t)(g->pad_t - r);
-    }
-  tap_begin[1] = nt;
-  return run_tc(dy, g->N, g->P, g->Q, g->K, false, packed, g->C, 1, tap_begin, taps, g->H, g->W, false, out_dc, out_da,
-                g->C, nullptr, dx, st);
+  if (g->transposed)  // dx[ih] = sum dy[stride*ih - pad + r] w: gather over dy
+    return tc_gather(dy, g->N, g->P, g->Q, g->K, g->R, g->S, g->stride, g->pad_t, g->pad_l, packed, g->C, g->H, g->W, nullptr,
+                     dx, st);
+  return tc_scatter(dy, g->N, g->P, g->Q, g->K, g->R, g->S, g->stride, g->pad_t, g->pad_l, packed, g->C, g->H, g->W, nullptr,
+                    dx, st);
 }
 
 }  // namespace b200gan

@@ -26,11 +26,12 @@ constexpr int WG_CHUNK_BYTES = WG_PIX * 128;  // one 32-channel chunk of one sta
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_JOBS = 52;
 
+// One job = one filter tap (or one (phase, tap) pair of the upsample fold).  "S" is the operand that is shifted by
+// the tap (x for Conv2d, dy for ConvTranspose2d), "D" the one that is read at the loop pixel.
 struct WgJob {
-  int16_t dc;          // dy channel base (phase view: b*K)
-  int8_t da;           // dy phase row
-  int8_t dw, dh;       // x shift
-  int8_t pad_[3];
+  int16_t s_dc, d_dc;  // channel base in the parity / phase view
+  int8_t s_da, d_da;   // row-parity coordinate in the view
+  int8_t s_dw, s_dh;   // shift of S in (view) pixels
 };
 
 struct WgParams {
@@ -39,7 +40,7 @@ struct WgParams {
   int32_t bw_log2, bh_log2;       // 32-pixel box = BW x BH
   int32_t tiles_w, tiles_h, N;    // pixel tiles per image
   int32_t tiles_total, tiles_per_split;
-  int32_t x_is_a;                 // 1: A = x (M' = Cin), B = dy (N' = Cout); 0: A = dy, B = x
+  int32_t s_is_a;                 // 1: A = shifted operand S, B = D; 0: A = D, B = S
   int32_t mtiles, ntiles;         // tiles of the (M', N') output
   int32_t ldn;                    // N' total (row length of a partial matrix)
   int32_t mtotal;                 // M' total
@@ -88,13 +89,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       const WgJob jb = p.jobs[job];
-      const CUtensorMap *mapA = p.x_is_a ? &tmX : &tmY;
-      const CUtensorMap *mapB = p.x_is_a ? &tmY : &tmX;
-      // per-operand coordinate recipe: x is shifted by the tap, dy sits in its phase
-      const int a_dc = p.x_is_a ? 0 : jb.dc, a_dw = p.x_is_a ? jb.dw : 0, a_da = p.x_is_a ? 0 : jb.da,
-                a_dh = p.x_is_a ? jb.dh : 0;
-      const int b_dc = p.x_is_a ? jb.dc : 0, b_dw = p.x_is_a ? 0 : jb.dw, b_da = p.x_is_a ? jb.da : 0,
-                b_dh = p.x_is_a ? 0 : jb.dh;
+      const CUtensorMap *mapA = p.s_is_a ? &tmX : &tmY;   // tmX = shifted operand S, tmY = dense operand D
+      const CUtensorMap *mapB = p.s_is_a ? &tmY : &tmX;
+      const int a_dc = p.s_is_a ? jb.s_dc : jb.d_dc, a_da = p.s_is_a ? jb.s_da : jb.d_da;
+      const int a_dw = p.s_is_a ? jb.s_dw : 0, a_dh = p.s_is_a ? jb.s_dh : 0;
+      const int b_dc = p.s_is_a ? jb.d_dc : jb.s_dc, b_da = p.s_is_a ? jb.d_da : jb.s_da;
+      const int b_dw = p.s_is_a ? 0 : jb.s_dw, b_dh = p.s_is_a ? 0 : jb.s_dh;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
@@ -190,10 +190,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-// dw[k][c][r][s] = sum_splits sum_{jobs contributing to (r,s)} partial[split][job][m'][n'],
-// (m', n') = (c, k) if x_is_a else (k, c).
+// dw = fold of partial[job][m'][n'] into the parameter layout (Conv2d [K][C][R][S], ConvTranspose2d [C][K][R][S]).
 struct WgReduceP {
-  int32_t K, C, R, S, nsplits, njobs, x_is_a, up2;
+  int32_t K, C, R, S, njobs, s_is_a, up2, transposed;
   int32_t mtotal, ldn;
 };
 __device__ __forceinline__ bool up2_contrib(int r, int a, int d) {
@@ -205,27 +204,29 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, float *__
   int64_t total = (int64_t)p.K * p.C * p.R * p.S;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    // iterate with c fastest so that reads of partial[..][k][c] (or [c][k]) stay reasonably coalesced
+    // c fastest so that reads of partial[..][k][c] (or [c][k]) stay reasonably coalesced
     int c = (int)(i % p.C);
     int64_t t = i / p.C;
     int k = (int)(t % p.K);
     t /= p.K;
     int s = (int)(t % p.S), r = (int)(t / p.S);
-    int64_t elem = p.x_is_a ? (int64_t)c * p.ldn + k : (int64_t)k * p.ldn + c;
+    const int sch = p.transposed ? k : c;   // channel index inside the shifted operand S
+    const int dch = p.transposed ? c : k;   // channel index inside the dense operand D
+    int64_t elem = p.s_is_a ? (int64_t)sch * p.ldn + dch : (int64_t)dch * p.ldn + sch;
     int64_t job_stride = (int64_t)p.mtotal * p.ldn;
+    const float *base = partial + elem;
     float acc = 0.f;
-    for (int sp = 0; sp < p.nsplits; ++sp) {
-      const float *base = partial + (int64_t)sp * p.njobs * job_stride + elem;
-      if (!p.up2) {
-        acc += __ldg(base + (int64_t)(r * p.S + s) * job_stride);
-      } else {
-        for (int j = 0; j < 16; ++j) {
-          int ph = j >> 2, tp = j & 3;
-          if (up2_contrib(r, ph >> 1, tp >> 1) && up2_contrib(s, ph & 1, tp & 1)) acc += __ldg(base + j * job_stride);
-        }
+    if (!p.up2) {
+      acc = __ldg(base + (int64_t)(r * p.S + s) * job_stride);
+    } else {
+      for (int j = 0; j < 16; ++j) {
+        int ph = j >> 2, tp = j & 3;
+        if (up2_contrib(r, ph >> 1, tp >> 1) && up2_contrib(s, ph & 1, tp & 1)) acc += __ldg(base + j * job_stride);
       }
     }
-    dw[(((int64_t)k * p.C + c) * p.R + r) * p.S + s] = acc;
+    const int64_t o = p.transposed ? (((int64_t)c * p.K + k) * p.R + r) * p.S + s
+                                   : (((int64_t)k * p.C + c) * p.R + r) * p.S + s;
+    dw[o] = acc;
   }
 }
 
@@ -237,28 +238,40 @@ static int ilog2c(int v) {
 }
 
 struct WgPlan {
-  int x_is_a, NB, mtiles, ntiles, mtotal, ldn, njobs, bwl, bhl, tiles_w, tiles_h, tiles_total, nsplits, tps, Ho, Wo;
+  int s_is_a, NB, mtiles, ntiles, mtotal, ldn, njobs, bwl, bhl, tiles_w, tiles_h, tiles_total, nsplits, tps, Ho, Wo;
+  int sch, dch;  // channels of the shifted / dense operand
 };
 
 static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
-  if (g->transposed || g->stride != 1 || g->pad_mode != B200GAN_PAD_ZERO || g->N < 1) return false;
-  if (g->C % 32 || g->K % 32) return false;
+  if (g->pad_mode != B200GAN_PAD_ZERO || g->N < 1) return false;
+  if (g->stride != 1 && g->stride != 2) return false;
+  if (g->C % 32 || g->K % 32 || 2 * g->C > 32767 || 2 * g->K > 32767) return false;
   const bool up2 = g->up == 2;
-  if (up2 && !(g->R == 3 && g->S == 3 && g->pad_t == 1 && g->pad_l == 1 && g->pad_b == 1 && g->pad_r == 1)) return false;
-  if (g->R * g->S > WG_MAX_JOBS || g->pad_t > 100 || g->pad_l > 100) return false;
-  // A = the operand with a multiple of 128 channels; B = the other (multiple of 64)
-  if (g->K % 128 == 0 && g->C % 64 == 0) pl.x_is_a = 0;
-  else if (g->C % 128 == 0 && g->K % 64 == 0) pl.x_is_a = 1;
+  if (up2 && (g->transposed || g->stride != 1 ||
+              !(g->R == 3 && g->S == 3 && g->pad_t == 1 && g->pad_l == 1 && g->pad_b == 1 && g->pad_r == 1)))
+    return false;
+  if (g->R * g->S > WG_MAX_JOBS || g->R > 15 || g->S > 15 || g->pad_t > 15 || g->pad_l > 15) return false;
+  // shifted operand S (x / dy for ConvTranspose2d) and dense operand D
+  pl.sch = g->transposed ? g->K : g->C;
+  pl.dch = g->transposed ? g->C : g->K;
+  if (g->stride == 2) {
+    const int Hf = g->transposed ? g->P : g->H, Wf = g->transposed ? g->Q : g->W;  // S is the full-resolution side
+    if ((Hf & 1) || (Wf & 1)) return false;
+  }
+  // A = the operand with a multiple of 128 channels; B = the other (multiple of 32)
+  if (pl.dch % 128 == 0) pl.s_is_a = 0;
+  else if (pl.sch % 128 == 0) pl.s_is_a = 1;
   else return false;
-  const int mch = pl.x_is_a ? g->C : g->K, nch = pl.x_is_a ? g->K : g->C;
-  pl.NB = nch % 128 == 0 ? 128 : 64;
+  const int mch = pl.s_is_a ? pl.sch : pl.dch, nch = pl.s_is_a ? pl.dch : pl.sch;
+  pl.NB = nch % 128 == 0 ? 128 : (nch % 64 == 0 ? 64 : 32);
   pl.mtotal = mch;
   pl.ldn = nch;
   pl.mtiles = mch / 128;
   pl.ntiles = nch / pl.NB;
   pl.njobs = up2 ? 16 : g->R * g->S;
-  pl.Ho = up2 ? g->H : g->P;  // pixel grid the contraction runs over (low-res grid for the fold)
-  pl.Wo = up2 ? g->W : g->Q;
+  // pixel grid the contraction runs over = grid of the dense operand (low-res grid for the upsample fold)
+  pl.Ho = up2 ? g->H : (g->transposed ? g->H : g->P);
+  pl.Wo = up2 ? g->W : (g->transposed ? g->W : g->Q);
   pl.bwl = ilog2c(pl.Wo);
   if (pl.bwl > 5) pl.bwl = 5;
   pl.bhl = ilog2c(pl.Ho);
@@ -311,53 +324,66 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   B2_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)ws % 16 == 0),
                "tcgen05 wgrad: pointers must be 16-byte aligned");
   const bool up2 = g->up == 2;
+  const int st2 = g->stride == 2;
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.njobs = pl.njobs;
   if (up2) {
+    // S = x (plain, shifted), D = dy through the phase view {2K, Q/2, 2, P/2, N}
     for (int ph = 0; ph < 4; ++ph)
       for (int tp = 0; tp < 4; ++tp) {
         int a = ph >> 1, b = ph & 1, dr = tp >> 1, ds = tp & 1;
         WgJob &j = p.jobs[ph * 4 + tp];
-        j.dc = (int16_t)(b * g->K); j.da = (int8_t)a; j.dh = (int8_t)(a - 1 + dr); j.dw = (int8_t)(b - 1 + ds);
+        j.d_dc = (int16_t)(b * g->K); j.d_da = (int8_t)a; j.s_dh = (int8_t)(a - 1 + dr); j.s_dw = (int8_t)(b - 1 + ds);
       }
   } else {
     for (int r = 0; r < g->R; ++r)
-      for (int s = 0; s < g->S; ++s) {
-        WgJob &j = p.jobs[r * g->S + s];
-        j.dc = 0; j.da = 0; j.dh = (int8_t)(r - g->pad_t); j.dw = (int8_t)(s - g->pad_l);
+      for (int s2 = 0; s2 < g->S; ++s2) {
+        WgJob &j = p.jobs[r * g->S + s2];
+        const int eh = r - g->pad_t, ew = s2 - g->pad_l;
+        if (!st2) {
+          j.s_dh = (int8_t)eh; j.s_dw = (int8_t)ew;
+        } else {  // S[2p + e] through the parity view {2Cs, Wf/2, 2, Hf/2, N}
+          j.s_dh = (int8_t)(eh >= 0 ? eh / 2 : -((-eh + 1) / 2)); j.s_da = (int8_t)(eh & 1);
+          j.s_dw = (int8_t)(ew >= 0 ? ew / 2 : -((-ew + 1) / 2)); j.s_dc = (int16_t)((ew & 1) * pl.sch);
+        }
       }
   }
   p.bw_log2 = pl.bwl; p.bh_log2 = pl.bhl;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.N = g->N;
   p.tiles_total = pl.tiles_total; p.tiles_per_split = pl.tps;
-  p.x_is_a = pl.x_is_a; p.mtiles = pl.mtiles; p.ntiles = pl.ntiles; p.ldn = pl.ldn; p.mtotal = pl.mtotal;
+  p.s_is_a = pl.s_is_a; p.mtiles = pl.mtiles; p.ntiles = pl.ntiles; p.ldn = pl.ldn; p.mtotal = pl.mtotal;
   p.partial = ws;
   p.lbo = WG_CHUNK_BYTES;
   p.sbo = 512;
-  if (const char *v = getenv("B200GAN_WG_VARIANT")) {  // bring-up switch for the MN-major descriptor fields
-    if (v[0] == '1') { p.lbo = 512; p.sbo = WG_CHUNK_BYTES; }
-  }
 
+  // operand tensors: Conv2d: S = x [N][H][W][C], D = dy [N][P][Q][K]; ConvTranspose2d: S = dy, D = x
+  const float *sptr = g->transposed ? dy : x, *dptr = g->transposed ? x : dy;
+  const uint64_t Hs = g->transposed ? g->P : g->H, Ws = g->transposed ? g->Q : g->W, Cs = pl.sch;
+  const uint64_t Hd = g->transposed ? g->H : g->P, Wd = g->transposed ? g->W : g->Q, Cd = pl.dch;
   CUtensorMap tmX, tmY;
   const uint32_t box[5] = {32, (uint32_t)(1 << pl.bwl), 1, (uint32_t)(1 << pl.bhl), 1};
   {
-    uint64_t dims[5] = {(uint64_t)g->C, (uint64_t)g->W, 1, (uint64_t)g->H, (uint64_t)g->N};
-    uint64_t strides[4] = {(uint64_t)g->C * 4, (uint64_t)g->W * g->C * 4, (uint64_t)g->W * g->C * 4,
-                           (uint64_t)g->H * g->W * g->C * 4};
-    if (int e = make_tmap_f32(&tmX, x, 5, dims, strides, box, 1)) return e;
+    uint64_t dims[5], strides[4];
+    if (!st2) {
+      dims[0] = Cs; dims[1] = Ws; dims[2] = 1; dims[3] = Hs; dims[4] = g->N;
+      strides[0] = Cs * 4; strides[1] = Ws * Cs * 4; strides[2] = Ws * Cs * 4; strides[3] = Hs * Ws * Cs * 4;
+    } else {
+      dims[0] = 2 * Cs; dims[1] = Ws / 2; dims[2] = 2; dims[3] = Hs / 2; dims[4] = g->N;
+      strides[0] = 2 * Cs * 4; strides[1] = Ws * Cs * 4; strides[2] = 2 * Ws * Cs * 4; strides[3] = Hs * Ws * Cs * 4;
+    }
+    if (int e = make_tmap_f32(&tmX, sptr, 5, dims, strides, box, 1)) return e;
   }
   {
     uint64_t dims[5], strides[4];
-    const uint64_t K = g->K, P = g->P, Q = g->Q;
     if (!up2) {
-      dims[0] = K; dims[1] = Q; dims[2] = 1; dims[3] = P; dims[4] = g->N;
-      strides[0] = K * 4; strides[1] = Q * K * 4; strides[2] = Q * K * 4; strides[3] = P * Q * K * 4;
+      dims[0] = Cd; dims[1] = Wd; dims[2] = 1; dims[3] = Hd; dims[4] = g->N;
+      strides[0] = Cd * 4; strides[1] = Wd * Cd * 4; strides[2] = Wd * Cd * 4; strides[3] = Hd * Wd * Cd * 4;
     } else {
-      dims[0] = 2 * K; dims[1] = Q / 2; dims[2] = 2; dims[3] = P / 2; dims[4] = g->N;
-      strides[0] = 2 * K * 4; strides[1] = Q * K * 4; strides[2] = 2 * Q * K * 4; strides[3] = P * Q * K * 4;
+      dims[0] = 2 * Cd; dims[1] = Wd / 2; dims[2] = 2; dims[3] = Hd / 2; dims[4] = g->N;
+      strides[0] = 2 * Cd * 4; strides[1] = Wd * Cd * 4; strides[2] = 2 * Wd * Cd * 4; strides[3] = Hd * Wd * Cd * 4;
     }
-    if (int e = make_tmap_f32(&tmY, dy, 5, dims, strides, box, 1)) return e;
+    if (int e = make_tmap_f32(&tmY, dptr, 5, dims, strides, box, 1)) return e;
   }
   CUtensorMap tmP;
   {
@@ -368,11 +394,12 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   }
   B2_CUDA(cudaMemsetAsync(ws, 0, (size_t)pl.njobs * pl.mtotal * pl.ldn * sizeof(float), st));
   dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
-  int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, tmP, p, grid, st) : launch_wg<64, 4>(tmX, tmY, tmP, p, grid, st);
+  int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, tmP, p, grid, st)
+                        : (pl.NB == 64 ? launch_wg<64, 4>(tmX, tmY, tmP, p, grid, st) : launch_wg<32, 4>(tmX, tmY, tmP, p, grid, st));
   if (rc) return rc;
   WgReduceP rp;
-  rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.nsplits = 1; rp.njobs = pl.njobs;
-  rp.x_is_a = pl.x_is_a; rp.up2 = up2 ? 1 : 0; rp.mtotal = pl.mtotal; rp.ldn = pl.ldn;
+  rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.njobs = pl.njobs;
+  rp.s_is_a = pl.s_is_a; rp.up2 = up2 ? 1 : 0; rp.transposed = g->transposed ? 1 : 0; rp.mtotal = pl.mtotal; rp.ldn = pl.ldn;
   int64_t total = (int64_t)g->K * g->C * g->R * g->S;
   unsigned blocks = (unsigned)(ceil_div64(total, 256) > 2368 ? 2368 : ceil_div64(total, 256));
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, rp);

@@ -14,6 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "pytorch-gan_b200"))
 
 CASES = [
+    dict(name="s2 k3 64->128 16x16 n4", cin=64, cout=128, k=3, pad=1, h=16, w=16, n=4, up=1, stride=2),
+    dict(name="s2 k4 128->256 32x32 n2", cin=128, cout=256, k=4, pad=1, h=32, w=32, n=2, up=1, stride=2),
+    dict(name="s2 k3 32->64 16x16 n8 (BN=32 dgrad)", cin=32, cout=64, k=3, pad=1, h=16, w=16, n=8, up=1, stride=2),
+    dict(name="convT k4 s2 256->128 8x8 n2", cin=256, cout=128, k=4, pad=1, h=8, w=8, n=2, up=1, stride=2, transposed=True),
+    dict(name="convT k4 s2 64->32 8x8 n3", cin=64, cout=32, k=4, pad=1, h=8, w=8, n=3, up=1, stride=2, transposed=True),
     dict(name="fprop 64->64 3x3 16x16 n2", cin=64, cout=64, k=3, pad=1, h=16, w=16, n=2, up=1),
     dict(name="fprop 64->128 3x3 8x8 n3", cin=64, cout=128, k=3, pad=1, h=8, w=8, n=3, up=1),
     dict(name="fprop 128->128 3x3 32x32 n2", cin=128, cout=128, k=3, pad=1, h=32, w=32, n=2, up=1),
@@ -31,12 +36,15 @@ def run_case(c):
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
     n, cin, cout, k, pad, h, w, up = c["n"], c["cin"], c["cout"], c["k"], c["pad"], c["h"], c["w"], c["up"]
+    stride, tr = c.get("stride", 1), c.get("transposed", False)
     x = torch.randn(n, cin, h, w, device="cuda").contiguous(memory_format=torch.channels_last)
-    wt = torch.randn(cout, cin, k, k, device="cuda") * 0.05
-    g, oshape = ops.make_geom(tuple(x.shape), tuple(wt.shape), 1, (pad, pad, pad, pad), 0, up, False)
+    wt = torch.randn(*((cin, cout, k, k) if tr else (cout, cin, k, k)), device="cuda") * 0.05
+    g, oshape = ops.make_geom(tuple(x.shape), tuple(wt.shape), stride, (pad, pad, pad, pad), 0, up, tr)
+    F = torch.nn.functional
+    conv = (lambda a, b: F.conv_transpose2d(a, b, None, stride, pad)) if tr else (lambda a, b: F.conv2d(a, b, None, stride, pad))
     print("  tc_supported fprop/dgrad:", ops.tc_supported(g, 0), ops.tc_supported(g, 1), "out", oshape, flush=True)
     xin = torch.nn.functional.interpolate(x, scale_factor=2) if up == 2 else x
-    ref = torch.nn.functional.conv2d(xin, wt, None, 1, pad)
+    ref = conv(xin, wt)
     y_s = ops.conv_fprop(g, x, ops.pack_weights(g, wt, PACK_SIMT_FPROP), ALGO_SIMT)
     torch.cuda.synchronize()
 
@@ -56,7 +64,7 @@ def run_case(c):
         print("  ours", y_t.flatten()[:6].tolist(), "\n  ref ", ref.flatten()[:6].tolist())
     dy = torch.randn_like(ref).contiguous(memory_format=torch.channels_last)
     xin_r = xin.clone().requires_grad_(True)
-    torch.nn.functional.conv2d(xin_r, wt, None, 1, pad).backward(dy)
+    conv(xin_r, wt).backward(dy)
     dref = xin_r.grad
     if up == 2:
         dref = dref.view(n, cin, h, 2, w, 2).sum(dim=(3, 5))
@@ -65,9 +73,8 @@ def run_case(c):
     dx_t = ops.conv_dgrad(g, dy, ops.pack_weights(g, wt, PACK_TC_DGRAD_UP2 if up == 2 else PACK_TC_DGRAD), ALGO_TC)
     torch.cuda.synchronize()
     print(f"  TC   dgrad rel err: {rel(dx_t, dref):.3e}", flush=True)
-    wref = torch.autograd.grad(torch.nn.functional.conv2d(xin, wt.clone().requires_grad_(True), None, 1, pad), [], dy) if False else None
     w_r = wt.clone().requires_grad_(True)
-    torch.nn.functional.conv2d(xin, w_r, None, 1, pad).backward(dy)
+    conv(xin, w_r).backward(dy)
     dw_s, _ = ops.conv_wgrad(g, x, dy, tuple(wt.shape), False, ALGO_SIMT)
     print(f"  SIMT wgrad rel err: {rel(dw_s, w_r.grad):.3e}", flush=True)
     if ops.tc_supported(g, 2):
