@@ -88,6 +88,80 @@ def wgan_gp_generator_step(generator, discriminator, opt_g, z):
     return g_loss.detach()
 
 
+def pix2pix_step(generator, discriminator, opt_g, opt_d, real_a, real_b, lambda_pixel=100.0):
+    """implementations/pix2pix/pix2pix.py:131-172 (MSE GAN loss :50, L1 pixel loss :51,:54)."""
+    mse, l1 = torch.nn.functional.mse_loss, torch.nn.functional.l1_loss
+    opt_g.zero_grad()                                          # :138
+    fake_b = generator(real_a)                                 # :141
+    with frozen(discriminator):
+        pred_fake = discriminator(fake_b, real_a)              # :142
+        valid = torch.ones_like(pred_fake)                     # :131
+        loss_g = mse(pred_fake, valid) + lambda_pixel * l1(fake_b, real_b)   # :143-148
+        loss_g.backward()                                      # :150
+    opt_g.step()                                               # :152
+    opt_d.zero_grad()                                          # :158
+    loss_real = mse(discriminator(real_b, real_a), valid)      # :161-162
+    loss_fake = mse(discriminator(fake_b.detach(), real_a), torch.zeros_like(valid))   # :165-166
+    loss_d = 0.5 * (loss_real + loss_fake)                     # :169
+    loss_d.backward()                                          # :171
+    opt_d.step()                                               # :172
+    return loss_g.detach(), loss_d.detach()
+
+
+class ReplayBuffer:
+    """History of generated images (cyclegan/utils.py:13-33): each incoming sample is either passed through or
+    swapped with a stored one (python `random`, per sample) -- index bookkeeping only, bit-exact."""
+
+    def __init__(self, max_size=50):
+        assert max_size > 0
+        self.max_size, self.data = max_size, []
+
+    def push_and_pop(self, data):
+        import random
+        out = []
+        for element in data.detach():
+            element = element.unsqueeze(0)
+            if len(self.data) < self.max_size:
+                self.data.append(element)
+                out.append(element)
+            elif random.uniform(0, 1) > 0.5:
+                i = random.randint(0, self.max_size - 1)
+                out.append(self.data[i].clone())
+                self.data[i] = element
+            else:
+                out.append(element)
+        return torch.cat(out)
+
+
+def cyclegan_step(g_ab, g_ba, d_a, d_b, opt_g, opt_d_a, opt_d_b, real_a, real_b, buf_a=None, buf_b=None,
+                  lambda_cyc=10.0, lambda_id=5.0):
+    """implementations/cyclegan/cyclegan.py:163-241: 6 generator passes + 2 D passes for the G loss, then one
+    step per discriminator on (real, replayed fake).  buf_* = ReplayBuffer or None (fakes used directly)."""
+    mse, l1 = torch.nn.functional.mse_loss, torch.nn.functional.l1_loss
+    opt_g.zero_grad()                                                          # :177
+    loss_identity = (l1(g_ba(real_a), real_a) + l1(g_ab(real_b), real_b)) / 2  # :180-183
+    fake_b = g_ab(real_a)                                                      # :186
+    fake_a = g_ba(real_b)                                                      # :188
+    with frozen(d_a), frozen(d_b):
+        pred_b, pred_a = d_b(fake_b), d_a(fake_a)
+        valid = torch.ones_like(pred_b)                                        # :166
+        loss_gan = (mse(pred_b, valid) + mse(pred_a, valid)) / 2               # :187-191
+        loss_cycle = (l1(g_ba(fake_b), real_a) + l1(g_ab(fake_a), real_b)) / 2  # :194-199
+        loss_g = loss_gan + lambda_cyc * loss_cycle + lambda_id * loss_identity  # :202
+        loss_g.backward()                                                      # :204
+    opt_g.step()                                                               # :205
+    fake = torch.zeros_like(valid)                                             # :167
+    losses_d = []
+    for d, opt, real, fk, buf in ((d_a, opt_d_a, real_a, fake_a, buf_a), (d_b, opt_d_b, real_b, fake_b, buf_b)):
+        opt.zero_grad()                                                        # :211 / :228
+        fk_ = buf.push_and_pop(fk) if buf is not None else fk.detach()         # :216 / :233
+        loss_d = (mse(d(real), valid) + mse(d(fk_.detach()), fake)) / 2        # :214-219
+        loss_d.backward()                                                      # :221
+        opt.step()                                                             # :222
+        losses_d.append(loss_d.detach())
+    return loss_g.detach(), (losses_d[0] + losses_d[1]) / 2
+
+
 class GraphedStep:
     """Capture one training step into a CUDA graph (static input/output buffers) and replay it.
     The step function must be free of host synchronisation; optimizers must be `capturable`."""

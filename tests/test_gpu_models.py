@@ -143,3 +143,44 @@ def test_models_vs_stock_torch_on_gpu(which):
         if pr.grad.double().norm().item() < 1e-6 or k.endswith("bias"):
             continue
         assert rel_err(po.grad, pr.grad) < 1e-2, k
+
+
+def test_pix2pix_and_cyclegan_steps_match_stock_torch():
+    """One full training step of each script body (pix2pix.py:131-172, cyclegan.py:163-241) with the drop-in modules
+    vs the same step on the oracle models (stock torch fp32): losses after the step's forward passes."""
+    import itertools
+    from b200gan import train, zoo
+    adam = lambda ps: torch.optim.Adam(ps, lr=2e-4, betas=(0.5, 0.999))  # noqa: E731
+    # pix2pix, batch 1 (Dropout active in the reference too -> compare in eval mode for G)
+    g_ref, d_ref = ref_models.build_pix2pix(2)
+    g, d = zoo.GeneratorUNet(), zoo.Pix2PixDiscriminator()
+    g.load_state_dict(g_ref.state_dict()); d.load_state_dict(d_ref.state_dict())
+    g_ref, d_ref, g, d = g_ref.cuda().eval(), d_ref.cuda(), g.cuda().eval(), d.cuda()
+    a = ref_models.synthetic_images(1, 3, 256, 256, seed=5).cuda()
+    b = ref_models.synthetic_images(1, 3, 256, 256, seed=6).cuda()
+    lg_r, ld_r = train.pix2pix_step(g_ref, d_ref, adam(g_ref.parameters()), adam(d_ref.parameters()), a, b)
+    lg, ld = train.pix2pix_step(g, d, adam(g.parameters()), adam(d.parameters()), a, b)
+    assert abs(lg.item() - lg_r.item()) < 2 * TOL * abs(lg_r.item())
+    assert abs(ld.item() - ld_r.item()) < 2 * TOL * abs(ld_r.item())
+    # cyclegan, 64x64, 3 residual blocks, replay buffers seeded identically
+    import random
+    shape = (3, 64, 64)
+    refs = [m.cuda() for m in ref_models.build_cyclegan(shape, 3, 4)]
+    ours = [zoo.GeneratorResNet(shape, 3), zoo.GeneratorResNet(shape, 3), zoo.CycleGANDiscriminator(shape),
+            zoo.CycleGANDiscriminator(shape)]
+    for m, r in zip(ours, refs):
+        m.load_state_dict(r.state_dict())
+        m.cuda()
+    a = ref_models.synthetic_images(2, 3, 64, 64, seed=7).cuda()
+    b = ref_models.synthetic_images(2, 3, 64, 64, seed=8).cuda()
+    res = []
+    for nets in (refs, ours):
+        random.seed(0)
+        og = adam(itertools.chain(nets[0].parameters(), nets[1].parameters()))
+        oa, ob = adam(nets[2].parameters()), adam(nets[3].parameters())
+        ba, bb = train.ReplayBuffer(), train.ReplayBuffer()
+        for _ in range(2):
+            out = train.cyclegan_step(*nets, og, oa, ob, a, b, ba, bb)
+        res.append(out)
+    assert abs(res[1][0].item() - res[0][0].item()) < 5 * TOL * abs(res[0][0].item())
+    assert abs(res[1][1].item() - res[0][1].item()) < 5 * TOL * abs(res[0][1].item())
