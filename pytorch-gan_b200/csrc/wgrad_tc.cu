@@ -39,6 +39,7 @@ struct WgParams {
   int32_t njobs;
   int32_t bw_log2, bh_log2;       // 32-pixel box = BW x BH
   int32_t tiles_w, tiles_h, N;    // pixel tiles per image
+  int32_t imgs_per_box;           // 32 / (BW * BH)
   int32_t tiles_total, tiles_per_split;
   int32_t s_is_a;                 // 1: A = shifted operand S, B = D; 0: A = D, B = S
   int32_t mtiles, ntiles;         // tiles of the (M', N') output
@@ -102,7 +103,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int tw = t % p.tiles_w;
         t /= p.tiles_w;
         const int th = t % p.tiles_h;
-        const int n = t / p.tiles_h;
+        const int n = (t / p.tiles_h) * p.imgs_per_box;  // a 32-pixel box spans several images when H*W < 32
         const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t *sa = smem + stage * STAGE_BYTES;
@@ -240,6 +241,7 @@ static int ilog2c(int v) {
 struct WgPlan {
   int s_is_a, NB, mtiles, ntiles, mtotal, ldn, njobs, bwl, bhl, tiles_w, tiles_h, tiles_total, nsplits, tps, Ho, Wo;
   int sch, dch;  // channels of the shifted / dense operand
+  int ipb;
 };
 
 static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
@@ -278,7 +280,8 @@ static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
   if (pl.bhl > 5 - pl.bwl) pl.bhl = 5 - pl.bwl;
   pl.tiles_w = ceil_div(pl.Wo, 1 << pl.bwl);
   pl.tiles_h = ceil_div(pl.Ho, 1 << pl.bhl);
-  int64_t tt = (int64_t)g->N * pl.tiles_w * pl.tiles_h;
+  pl.ipb = 32 >> (pl.bwl + pl.bhl);  // images per 32-pixel box (>1 only when the whole map has < 32 pixels)
+  int64_t tt = (int64_t)ceil_div(g->N, pl.ipb) * pl.tiles_w * pl.tiles_h;
   if (tt > (1 << 30)) return false;
   pl.tiles_total = (int)tt;
   int ctas_per_split = pl.njobs * pl.mtiles * pl.ntiles;
@@ -350,7 +353,7 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
       }
   }
   p.bw_log2 = pl.bwl; p.bh_log2 = pl.bhl;
-  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.N = g->N;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.N = g->N; p.imgs_per_box = pl.ipb;
   p.tiles_total = pl.tiles_total; p.tiles_per_split = pl.tps;
   p.s_is_a = pl.s_is_a; p.mtiles = pl.mtiles; p.ntiles = pl.ntiles; p.ldn = pl.ldn; p.mtotal = pl.mtotal;
   p.partial = ws;
@@ -362,7 +365,7 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   const uint64_t Hs = g->transposed ? g->P : g->H, Ws = g->transposed ? g->Q : g->W, Cs = pl.sch;
   const uint64_t Hd = g->transposed ? g->H : g->P, Wd = g->transposed ? g->W : g->Q, Cd = pl.dch;
   CUtensorMap tmX, tmY;
-  const uint32_t box[5] = {32, (uint32_t)(1 << pl.bwl), 1, (uint32_t)(1 << pl.bhl), 1};
+  const uint32_t box[5] = {32, (uint32_t)(1 << pl.bwl), 1, (uint32_t)(1 << pl.bhl), (uint32_t)pl.ipb};
   {
     uint64_t dims[5], strides[4];
     if (!st2) {

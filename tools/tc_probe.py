@@ -14,6 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "pytorch-gan_b200"))
 
 CASES = [
+    dict(name="DCGAN D conv4 s2 k3 64->128 8x8 n16 (16-pixel grid)", cin=64, cout=128, k=3, pad=1, h=8, w=8, n=16, up=1, stride=2),
+    dict(name="convT k4 s2 512->64 2x2 n2 (4-pixel grid)", cin=512, cout=64, k=4, pad=1, h=2, w=2, n=2, up=1, stride=2, transposed=True),
+    dict(name="pix2pix down8 k4 s2 512->512 2x2 n3", cin=512, cout=512, k=4, pad=1, h=2, w=2, n=3, up=1, stride=2),
     dict(name="s2 k3 64->128 16x16 n4", cin=64, cout=128, k=3, pad=1, h=16, w=16, n=4, up=1, stride=2),
     dict(name="s2 k4 128->256 32x32 n2", cin=128, cout=256, k=4, pad=1, h=32, w=32, n=2, up=1, stride=2),
     dict(name="s2 k3 32->64 16x16 n8 (BN=32 dgrad)", cin=32, cout=64, k=3, pad=1, h=16, w=16, n=8, up=1, stride=2),
@@ -95,7 +98,7 @@ if __name__ == "__main__":
     for c in CASES:
         print("==", c["name"], flush=True)
         try:
-            r = subprocess.run([sys.executable, __file__, json.dumps(c)], timeout=120, capture_output=True, text=True)
+            r = subprocess.run([sys.executable, __file__, json.dumps(c)], timeout=60, capture_output=True, text=True)
             print(r.stdout, end="")
             if r.returncode != 0:
                 print("  EXIT", r.returncode, r.stderr[-1500:])
