@@ -30,6 +30,9 @@ for p in (ROOT, os.path.join(ROOT, "pytorch-gan_b200")):
 IMG, BATCH, LATENT = 64, 128, 100
 # useful conv/linear FLOPs of one DCGAN step at bs 128 (reference formulation)
 GFLOP_PER_STEP_REFERENCE_FORM = 359.0
+# dram__bytes_read.sum + dram__bytes_write.sum of conv_tc_kernel<64,4> on this workload from the committed
+# `ncu --set full` capture (profiles/): 159 MB read + 99 MB written per launch (algorithmic: 67 + 134 MB)
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 258.0e6
 
 
 def parse_args():
@@ -139,32 +142,44 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-def time_conv_kernel(torch, iters=20):
-    """Roofline leg: the tcgen05 conv kernel alone -- G conv2 of the step (Upsample+Conv 128->64 on
-    [128,128,32,32], dcgan.py:58-59) as the folded 4-phase implicit GEMM.  Executed FLOPs (after the
-    2.25x upsample fold) / CUDA-event time.  In+out = 67+134 MB > L2, so no flush is needed."""
-    from b200gan import ops
-    from b200gan._lib import ALGO_TC, PACK_TC_FPROP_UP2
-    x = torch.randn(BATCH, 128, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
-    w = torch.randn(64, 128, 3, 3, device="cuda") * 0.02
-    g, _ = ops.make_geom(tuple(x.shape), tuple(w.shape), 1, (1, 1, 1, 1), 0, 2, False)
-    if not ops.tc_supported(g, 0):
-        return None
-    packed = ops.pack_weights(g, w, PACK_TC_FPROP_UP2)
+def _event_time(torch, fn, iters):
     for _ in range(3):
-        ops.conv_fprop(g, x, packed, ALGO_TC)
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        ops.conv_fprop(g, x, packed, ALGO_TC)
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    return e0.elapsed_time(e1) / iters
+
+
+def time_conv_kernel(torch, iters=20):
+    """Roofline leg: the tcgen05 kernels alone on G conv2 of the step (Upsample + Conv 128->64 on [128,128,32,32],
+    dcgan.py:58-59) as the folded 4-phase implicit GEMM.  Executed FLOPs (after the 2.25x upsample fold) /
+    CUDA-event time.  In + out = 67 + 134 MB > L2, so no flush is needed between launches."""
+    from b200gan import ops
+    from b200gan._lib import ALGO_TC, PACK_TC_DGRAD_UP2, PACK_TC_FPROP_UP2
+    x = torch.randn(BATCH, 128, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    w = torch.randn(64, 128, 3, 3, device="cuda") * 0.02
+    g, oshape = ops.make_geom(tuple(x.shape), tuple(w.shape), 1, (1, 1, 1, 1), 0, 2, False)
+    if not ops.tc_supported(g, 0):
+        return None
+    dy = torch.randn(oshape, device="cuda").contiguous(memory_format=torch.channels_last)
+    pf, pd = ops.pack_weights(g, w, PACK_TC_FPROP_UP2), ops.pack_weights(g, w, PACK_TC_DGRAD_UP2)
     flops_exec = 2.0 * BATCH * 32 * 32 * 4 * 64 * 128 * 4  # 4 phases x 4 taps x Cin 128 x Cout 64 per low-res pixel
-    bytes_alg = (x.numel() + BATCH * 64 * 64 * 64 + packed.numel()) * 4
-    return {"ms": ms, "tflops": flops_exec / ms / 1e9, "gbs": bytes_alg / ms / 1e6, "flops": flops_exec,
-            "bytes": bytes_alg}
+    bytes_alg = (x.numel() + dy.numel() + pf.numel()) * 4
+    ms_f = _event_time(torch, lambda: ops.conv_fprop(g, x, pf, ALGO_TC), iters)
+    ms_d = _event_time(torch, lambda: ops.conv_dgrad(g, dy, pd, ALGO_TC), iters)
+    ms_w = _event_time(torch, lambda: ops.conv_wgrad(g, x, dy, tuple(w.shape), False, ALGO_TC), iters)
+    # context: cuBLAS TF32 GEMM on the same box (what "TF32 tensor peak" means in practice here)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device="cuda")
+    ms_g = _event_time(torch, lambda: a @ a, 5)
+    return {"ms": ms_f, "tflops": flops_exec / ms_f / 1e9, "gbs": bytes_alg / ms_f / 1e6, "flops": flops_exec,
+            "bytes": bytes_alg, "dgrad_tflops": flops_exec / ms_d / 1e9, "wgrad_tflops": flops_exec / ms_w / 1e9,
+            "cublas_tf32_gemm_tflops": 2 * 8192.0 ** 3 / ms_g / 1e9}
 
 
 def _finish(world):
@@ -285,7 +300,10 @@ def run_ours(args):
                     "bound": "tensor", "achieved": conv["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": conv["tflops"] / tf32_peak, "peak_source": peak_src + ", TF32 = bf16/2",
                     "ms_per_launch": conv["ms"], "algorithmic_gbs": conv["gbs"], "hbm_peak_gbs": hbm_peak,
-                    "traffic": None}
+                    "executed_gflop_per_launch": conv["flops"] / 1e9, "algorithmic_mbytes_per_launch": conv["bytes"] / 1e6,
+                    "same_layer_dgrad_tflops": conv["dgrad_tflops"], "same_layer_wgrad_tflops": conv["wgrad_tflops"],
+                    "cublas_tf32_gemm_8192_tflops": conv["cublas_tf32_gemm_tflops"],
+                    "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -144,6 +144,12 @@ int b200gan_epilogue_bwd(const float *dy, const float *y, const float *chan_scal
                          float slope, int64_t n, int32_t K, int64_t PQ, int32_t round_tf32,
                          float *dz, void *stream);
 
+/* db[k] = sum over (n,p,q) of dy * act'(y) * chan_scale -- the bias gradient of a fused conv block computed from
+ * UNROUNDED values (when dz is TF32-rounded for the tensor-core dgrad/wgrad, summing the rounded values loses the
+ * cancellation a bias gradient lives on).  db is overwritten. */
+int b200gan_bias_grad(const float *dy, const float *y, const float *chan_scale, int32_t act, float slope,
+                      int64_t rows, int32_t K, int64_t PQ, float *db, void *stream);
+
 /* ---- BatchNorm2d (training) / InstanceNorm2d ------------------------------------------ */
 /* Normalisation over groups: G = C (per_sample == 0: BatchNorm2d, dcgan.py:53,56,60,80) or
  * N*C (per_sample == 1: InstanceNorm2d, pix2pix/models.py:25,40,117, cyclegan/models.py:29...). */
@@ -162,8 +168,9 @@ typedef struct b200gan_norm_desc {
 int b200gan_norm_stats(const b200gan_norm_desc *d, const float *x, double *stats, void *stream);
 /* From stats: mean_rstd[2][G]; scale_shift[2][G] (= gamma*rstd, beta-mean*gamma*rstd; gamma,
  * beta may be NULL = 1,0); running_mean/var (may be NULL) updated with the UNBIASED variance,
- * num_batches_tracked (int64, may be NULL) += 1 -- torch.nn.BatchNorm2d semantics. */
-int b200gan_norm_finalize(const b200gan_norm_desc *d, const double *stats, const float *gamma,
+ * num_batches_tracked (int64, may be NULL) += 1 -- torch.nn.BatchNorm2d semantics.
+ * `stats` is CONSUMED: it is zeroed on return, so a persistent accumulator never needs a memset. */
+int b200gan_norm_finalize(const b200gan_norm_desc *d, double *stats, const float *gamma,
                           const float *beta, float *mean_rstd, float *scale_shift,
                           float *running_mean, float *running_var, int64_t *num_batches_tracked,
                           void *stream);
@@ -171,7 +178,7 @@ int b200gan_norm_finalize(const b200gan_norm_desc *d, const double *stats, const
 int b200gan_norm_apply(const b200gan_norm_desc *d, const float *x, const float *scale_shift,
                        float *y, void *stream);
 /* Backward.  Inputs: dy, saved input x, saved output y (only read when act != NONE),
- * mean_rstd, gamma (or NULL).  sums[2][G] fp64 zeroed by caller (workspace).
+ * mean_rstd, gamma (or NULL).  sums[2][G] fp64 workspace: zero on entry, handed back zeroed.
  * Outputs: dx; dgamma_dbeta[2][G] (only meaningful for per_sample == 0 with affine; may be NULL). */
 int b200gan_norm_bwd(const b200gan_norm_desc *d, const float *dy, const float *x, const float *y,
                      const float *mean_rstd, const float *gamma, double *sums, float *dx,

@@ -80,7 +80,7 @@ class ConvFn(torch.autograd.Function):
             packed = cache.get(g, w, PACK_SIMT_FPROP)
         stats = None
         if spec.stats is not None:
-            stats = torch.zeros(2 * (g.N * g.K if spec.stats else g.K), device=x.device, dtype=torch.float64)
+            stats = ops.zero_scratch(x.device, 2 * (g.N * g.K if spec.stats else g.K))
         fuse_stats = stats is not None and not (algo == ALGO_TC and spec.stats)
         y = ops.conv_fprop(g, x, packed, algo, bias=None if bias is None else bias.detach(), act=spec.act,
                            slope=spec.slope, chan_scale=chan_scale, stats=stats if fuse_stats else None,
@@ -116,9 +116,16 @@ class ConvFn(torch.autograd.Function):
             else:
                 packed = ctx.cache.get(g, w, PACK_SIMT_DGRAD)
                 dx = ops.conv_dgrad(g, dz, packed, ALGO_SIMT)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        if want_db and dz is not dy and spec.rtf_dz:
+            # dz was rounded to TF32 for the tensor-core passes; a bias gradient is a sum with heavy cancellation
+            # and must come from the unrounded values
+            db = ops.bias_grad(dy, y, chan_scale, spec.act, spec.slope)
+            want_db = False
+        if ctx.needs_input_grad[1] or want_db:
             algo = ALGO_SIMT if ops.Config.algo == "simt" else ALGO_AUTO
-            dw, db = ops.conv_wgrad(g, x, dz, tuple(weight.shape), ctx.has_bias and ctx.needs_input_grad[2], algo)
+            dw, db2 = ops.conv_wgrad(g, x, dz, tuple(weight.shape), want_db, algo)
+            db = db2 if want_db else db
             if not ctx.needs_input_grad[1]:
                 dw = None
         return dx, dw, db, None, None, None

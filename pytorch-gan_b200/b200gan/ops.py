@@ -159,6 +159,15 @@ def epilogue_bwd(dy, y, chan_scale, act, slope, round_tf32=False):
     return dz
 
 
+def bias_grad(dy, y, chan_scale, act, slope):
+    """Bias gradient of a fused conv block from unrounded values (see include/b200gan.h)."""
+    n, k, p, q = dy.shape
+    db = torch.empty(k, device=dy.device, dtype=torch.float32)
+    _lib.check(_lib.load().b200gan_bias_grad(dy.data_ptr(), _ptr(y), _ptr(chan_scale), act, slope, n * p * q, k, p * q,
+                                             db.data_ptr(), _stream()), "bias_grad")
+    return db
+
+
 # ---- normalisation -----------------------------------------------------------------------------
 def _norm_desc(x, per_sample, eps, momentum, act, slope, round_tf32):
     n, c, h, w = x.shape
@@ -168,9 +177,30 @@ def _norm_desc(x, per_sample, eps, momentum, act, slope, round_tf32):
     return d
 
 
+_zero_scratch = {}
+
+
+def zero_scratch(device, numel):
+    """Persistent fp64 accumulator that is zero whenever it is handed out: every kernel that consumes it
+    (norm_finalize, norm_bwd) zeroes it again, so no fill kernel is launched per use.  One buffer per
+    (device, size) suffices because producer -> consumer pairs never interleave on the stream."""
+    key = (device, numel)
+    t = _zero_scratch.get(key)
+    if t is None:
+        t = torch.zeros(numel, device=device, dtype=torch.float64)
+        _zero_scratch[key] = t
+    return t
+
+
+def reset_scratch():
+    """Re-zero the accumulators (only needed after an exception interrupted a producer/consumer pair)."""
+    for t in _zero_scratch.values():
+        t.zero_()
+
+
 def new_stats(x, per_sample):
     n, c = x.shape[0], x.shape[1]
-    return torch.zeros(2 * (n * c if per_sample else c), device=x.device, dtype=torch.float64)
+    return zero_scratch(x.device, 2 * (n * c if per_sample else c))
 
 
 def norm_forward(x, gamma, beta, running_mean, running_var, nbt, per_sample, eps, momentum, act=ACT_NONE, slope=0.0,
@@ -208,7 +238,7 @@ def norm_backward(dy, x, y, mean_rstd, gamma, per_sample, eps, act=ACT_NONE, slo
     lib = _lib.load()
     d = _norm_desc(x, per_sample, eps, 0.0, act, slope, round_tf32)
     groups = mean_rstd.numel() // 2
-    sums = torch.zeros(2 * groups, device=x.device, dtype=torch.float64)
+    sums = zero_scratch(x.device, 2 * groups)
     dx = torch.empty_like(x, memory_format=CL)
     dgb = torch.empty(2 * groups, device=x.device, dtype=torch.float32) if need_params else None
     _lib.check(lib.b200gan_norm_bwd(ctypes.byref(d), dy.data_ptr(), x.data_ptr(), _ptr(y), mean_rstd.data_ptr(),

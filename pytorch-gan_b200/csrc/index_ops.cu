@@ -175,6 +175,40 @@ __global__ void epilogue_bwd_kernel(const float *__restrict__ dy, const float *_
   }
 }
 
+// bias gradient of a fused conv block from unrounded values: db[k] = sum_m dy[m][k] act'(y[m][k]) cs[n(m)][k]
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const float *__restrict__ dy, const float *__restrict__ y, const float *__restrict__ chan_scale, int act,
+                 float slope, int64_t M, int K, int64_t PQ, int64_t rows_per_block, float *__restrict__ db) {
+  __shared__ float red[8][33];
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  float s = 0.f;
+  if (k < K)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      float d = __ldg(dy + r * K + k);
+      float cs = 1.f;
+      if (chan_scale) {
+        cs = __ldg(chan_scale + (r / PQ) * K + k);
+        d *= cs;
+      }
+      if (act != B200GAN_ACT_NONE) {
+        float yv = __ldg(y + r * K + k);
+        if (chan_scale && (act == B200GAN_ACT_TANH || act == B200GAN_ACT_SIGMOID)) yv = cs != 0.f ? yv / cs : 0.f;
+        d *= act_grad_from_out(yv, act, slope);
+      }
+      s += d;
+    }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(db + k, t);
+  }
+}
+
 // ---- Adam ---------------------------------------------------------------------------------------------
 // torch.optim.Adam (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  Step count lives on the device.
@@ -297,6 +331,24 @@ extern "C" int b200gan_adam_step(float *p, const float *g, float *m, float *v, i
     B2_LAUNCH_CHECK();
   }
   adam_step_inc_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_bias_grad(const float *dy, const float *y, const float *chan_scale, int32_t act, float slope,
+                                 int64_t rows, int32_t K, int64_t PQ, float *db, void *stream) {
+  B2_CHECK_ARG(dy && db, "bias_grad: null pointer");
+  B2_CHECK_ARG(act == B200GAN_ACT_NONE || y != nullptr, "bias_grad: activation needs the saved output");
+  cudaStream_t st = as_stream(stream);
+  B2_CUDA(cudaMemsetAsync(db, 0, (size_t)K * sizeof(float), st));
+  if (rows == 0) return B200GAN_OK;
+  int64_t yb = 148 * 8 / ceil_div(K, 32);
+  if (yb < 1) yb = 1;
+  int64_t rpb = ceil_div64(rows, yb);
+  if (rpb < 64) rpb = 64;
+  yb = ceil_div64(rows, rpb);
+  bias_grad_kernel<<<dim3((unsigned)ceil_div(K, 32), (unsigned)yb), dim3(32, 8), 0, st>>>(dy, y, chan_scale, act, slope, rows,
+                                                                                       K, PQ, rpb, db);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }

@@ -47,7 +47,7 @@ norm_stats_kernel(const float *__restrict__ x, double *__restrict__ stats, int C
   }
 }
 
-__global__ void norm_finalize_kernel(const double *__restrict__ stats, const float *__restrict__ gamma,
+__global__ void norm_finalize_kernel(double *__restrict__ stats, const float *__restrict__ gamma,
                                      const float *__restrict__ beta, float *__restrict__ mean_rstd,
                                      float *__restrict__ scale_shift, float *running_mean,
                                      float *running_var, int64_t *nbt, int G, int C, double count,
@@ -57,6 +57,8 @@ __global__ void norm_finalize_kernel(const double *__restrict__ stats, const flo
   if (g >= G) return;
   double mean = stats[g] / count;
   double var = stats[G + g] / count - mean * mean;
+  stats[g] = 0.0;      // the accumulator is consumed: leave it zeroed for its next use (no memset launch needed)
+  stats[G + g] = 0.0;
   if (var < 0.0) var = 0.0;
   float rstd = (float)(1.0 / sqrt(var + (double)eps));
   int c = g % C;
@@ -203,11 +205,15 @@ norm_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x,
   }
 }
 
-__global__ void norm_bwd_params_kernel(const double *__restrict__ sums, float *__restrict__ dgb, int G) {
+__global__ void norm_bwd_params_kernel(double *__restrict__ sums, float *__restrict__ dgb, int G) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
-  dgb[g] = (float)sums[G + g];  // dgamma = sum dy' * xhat
-  dgb[G + g] = (float)sums[g];  // dbeta  = sum dy'
+  if (dgb) {
+    dgb[g] = (float)sums[G + g];  // dgamma = sum dy' * xhat
+    dgb[G + g] = (float)sums[g];  // dbeta  = sum dy'
+  }
+  sums[g] = 0.0;  // workspace handed back zeroed
+  sums[G + g] = 0.0;
 }
 
 static void reduce_grid(const b200gan_norm_desc *d, dim3 &grid, int64_t &rows, int64_t &rpb) {
@@ -247,7 +253,7 @@ extern "C" int b200gan_norm_stats(const b200gan_norm_desc *d, const float *x, do
   return B200GAN_OK;
 }
 
-extern "C" int b200gan_norm_finalize(const b200gan_norm_desc *d, const double *stats,
+extern "C" int b200gan_norm_finalize(const b200gan_norm_desc *d, double *stats,
                                      const float *gamma, const float *beta, float *mean_rstd,
                                      float *scale_shift, float *running_mean, float *running_var,
                                      int64_t *num_batches_tracked, void *stream) {
@@ -315,9 +321,7 @@ extern "C" int b200gan_norm_bwd(const b200gan_norm_desc *d, const float *dy, con
         dy, x, y, mean_rstd, gamma, sums, dx, tv, d->C, d->HW, G, d->per_sample, inv_count, d->act,
         d->slope, d->round_tf32);
   B2_LAUNCH_CHECK();
-  if (dgamma_dbeta) {
-    norm_bwd_params_kernel<<<ceil_div(G, 128), 128, 0, st>>>(sums, dgamma_dbeta, G);
-    B2_LAUNCH_CHECK();
-  }
+  norm_bwd_params_kernel<<<ceil_div(G, 128), 128, 0, st>>>(sums, dgamma_dbeta, G);
+  B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
