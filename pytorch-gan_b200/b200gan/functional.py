@@ -57,6 +57,25 @@ class PackCache:
         return packed
 
 
+def _pow2ceil(v):
+    p = 1
+    while p < v:
+        p *= 2
+    return p
+
+
+def _tc_tile_is_one_image(g, spec):
+    """True when a 128-pixel tile of the tcgen05 fprop never spans two images, the condition for fusing
+    per-sample (InstanceNorm) sums into its epilogue (mirrors the tile choice in conv_tc.cu:run_tc)."""
+    if spec.up == 2:
+        ho, wo = g.H, g.W                 # per-phase grid of the upsample fold
+    elif spec.transposed and spec.stride == 2:
+        ho, wo = g.P // 2, g.Q // 2       # per-phase grid of the scatter form
+    else:
+        ho, wo = g.P, g.Q
+    return min(_pow2ceil(wo), 128) * _pow2ceil(ho) >= 128
+
+
 def _as_cl(t):
     return t if ops.is_cl(t) else ops.to_cl(t)
 
@@ -81,7 +100,7 @@ class ConvFn(torch.autograd.Function):
         stats = None
         if spec.stats is not None:
             stats = ops.zero_scratch(x.device, 2 * (g.N * g.K if spec.stats else g.K))
-        fuse_stats = stats is not None and not (algo == ALGO_TC and spec.stats)
+        fuse_stats = stats is not None and not (algo == ALGO_TC and spec.stats and not _tc_tile_is_one_image(g, spec))
         y = ops.conv_fprop(g, x, packed, algo, bias=None if bias is None else bias.detach(), act=spec.act,
                            slope=spec.slope, chan_scale=chan_scale, stats=stats if fuse_stats else None,
                            stats_per_sample=bool(spec.stats), round_tf32=spec.rtf_out)

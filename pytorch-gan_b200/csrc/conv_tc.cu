@@ -98,6 +98,8 @@ struct TcParams {
   const float *bias;
   const float *chan_scale;
   double *stats;
+  int32_t stats_groups;  // G: ldk (BatchNorm) or N*ldk (InstanceNorm: per-sample groups, tile = one image)
+  int32_t stats_per_sample;
   int32_t act;
   float slope;
   int32_t rtf;
@@ -322,8 +324,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           a += red[(qq * BN + e) * 2 + 0];
           b += red[(qq * BN + e) * 2 + 1];
         }
-        atomicAdd(p.stats + ntile * BN + e, (double)a);
-        atomicAdd(p.stats + p.ldk + ntile * BN + e, (double)b);
+        const int gidx = (p.stats_per_sample ? n0 * p.ldk : 0) + ntile * BN + e;
+        atomicAdd(p.stats + gidx, (double)a);
+        atomicAdd(p.stats + p.stats_groups + gidx, (double)b);
       }
     }
   }
@@ -437,6 +440,10 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   p.bias = ep ? ep->bias : nullptr;
   p.chan_scale = ep ? ep->chan_scale : nullptr;
   p.stats = ep ? ep->stats : nullptr;
+  p.stats_per_sample = ep ? ep->stats_per_sample : 0;
+  p.stats_groups = p.stats_per_sample ? N * ldk : ldk;
+  if (p.stats && p.stats_per_sample && BNn != 1)
+    B2_UNSUPPORTED("tcgen05 fprop: per-sample statistics need one image per tile (H*W >= 128 per phase)");
   p.act = ep ? ep->act : 0;
   p.slope = ep ? ep->slope : 0.f;
   p.rtf = ep ? ep->round_tf32 : 0;
@@ -568,11 +575,7 @@ static int tc_scatter(const float *in, int N, int Pi, int Qi, int Cc, int R, int
 int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
              cudaStream_t st) {
   b200gan_epilogue e2;
-  if (ep) {
-    e2 = *ep;
-    // per-sample (InstanceNorm) sums can only be fused when a tile never spans two images
-    if (e2.stats && e2.stats_per_sample) B2_UNSUPPORTED("tcgen05 fprop: per-sample statistics are not fused");
-  }
+  if (ep) e2 = *ep;
   const b200gan_epilogue *e = ep ? &e2 : nullptr;
   if (g->up == 2) {
     // phase (a,b): out[2i+a][2j+b] = sum_{dr,ds} x[i+a-1+dr][j+b-1+ds] * Wf[a][b][dr][ds]
