@@ -139,10 +139,18 @@ def test_models_vs_stock_torch_on_gpu(which):
     gy = torch.randn_like(yr)
     yr.backward(gy)
     yo.backward(gy)
-    for (k, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+    # yardstick: the same backward on stock torch with TF32 convolutions (the reference's default GPU path)
+    import copy
+    ref_t = copy.deepcopy(ref)
+    ref_t.zero_grad()
+    _set_tf32(True)
+    ref_t(*args).backward(gy)
+    _set_tf32(False)
+    for (k, po), (_, pr), (_, pt) in zip(ours.named_parameters(), ref.named_parameters(), ref_t.named_parameters()):
         if pr.grad.double().norm().item() < 1e-6 or k.endswith("bias"):
             continue
-        assert rel_err(po.grad, pr.grad) < 1e-2, k
+        bound = max(1e-2, 1.5 * rel_err(pt.grad, pr.grad))
+        assert rel_err(po.grad, pr.grad) < bound, f"{k}: bound {bound:.2e}"
 
 
 def test_pix2pix_and_cyclegan_steps_match_stock_torch():
