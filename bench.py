@@ -104,31 +104,42 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_step_throughput(steps, warmup, threads=None):
-    """The reference's own CPU path: oracle restatement of dcgan.py:146-183 with stock torch.nn."""
+def cpu_step_throughput(steps, warmup, threads=None, budget_s=150.0):
+    """The reference's own CPU path: oracle restatement of dcgan.py:146-183 with stock torch.nn.
+    Bounded sample: if `steps` full-batch steps would not fit in `budget_s`, every step processes a smaller batch
+    of the same workload (per-image CPU cost is batch-insensitive); images/s is reported either way."""
     import torch
     from oracle import ref_models
-    threads = threads or os.cpu_count() or 1
+    threads = threads or min(os.cpu_count() or 1, 32)   # more threads than that only add contention on this path
     torch.set_num_threads(threads)
     g, d = ref_models.build_dcgan(IMG, seed=0)
     og, od = ref_models.make_adam(g.parameters()), ref_models.make_adam(d.parameters())
-    imgs = ref_models.synthetic_images(BATCH, 1, IMG, IMG, seed=0)
-    z = ref_models.synthetic_z(BATCH, seed=0)
-    for _ in range(warmup):
+    batch = BATCH
+    imgs = ref_models.synthetic_images(batch, 1, IMG, IMG, seed=0)
+    z = ref_models.synthetic_z(batch, seed=0)
+    t0 = time.perf_counter()
+    ref_models.dcgan_step(g, d, og, od, imgs, z)          # first warm-up step doubles as the probe
+    t_probe = time.perf_counter() - t0
+    if (steps + max(warmup - 1, 0)) * t_probe > budget_s:
+        batch = int(BATCH * budget_s / ((steps + max(warmup - 1, 0)) * t_probe)) // 8 * 8
+        batch = max(8, min(BATCH, batch))
+        imgs, z = imgs[:batch], z[:batch]
+    for _ in range(max(warmup - 1, 0)):
         ref_models.dcgan_step(g, d, og, od, imgs, z)
     t0 = time.perf_counter()
     for _ in range(steps):
         ref_models.dcgan_step(g, d, og, od, imgs, z)
     dt = time.perf_counter() - t0
-    return BATCH * steps / dt, dt / steps, threads
+    return batch * steps / dt, dt / steps, threads, batch
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ips, spstep, threads = cpu_step_throughput(args.steps, args.warmup)
-    sample = f"{args.steps} full steps (bs {BATCH}, {IMG}x{IMG}) after {args.warmup} warm-up, stock torch CPU, {threads} threads"
+    ips, spstep, threads, batch = cpu_step_throughput(args.steps, max(args.warmup, 1))
+    sample = (f"{args.steps} steps of dcgan.py:146-183 on {batch} of the {BATCH} images per step ({IMG}x{IMG}) after "
+              f"{args.warmup} warm-up, stock torch CPU, {threads} threads")
     print(json.dumps({
         "impl": "reference", "metric": "DCGAN 64x64 images/sec (full G+D step)", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spstep * 1e3,
@@ -307,9 +318,10 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        ips, spstep, threads = cpu_step_throughput(3, 1)
+        ips, spstep, threads, batch = cpu_step_throughput(2, 1, budget_s=25.0)
         cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"3 full steps (bs {BATCH}) after 1 warm-up, oracle port of dcgan.py:146-183, stock torch CPU"}
+               "sample": f"2 steps on {batch} of the {BATCH} images per step after 1 warm-up, oracle port of "
+                         f"dcgan.py:146-183, stock torch CPU"}
 
     h2d = sum(t_.numel() * 4 for t_ in (host_imgs[0], host_z[0]))
     step_ms = ms / args.steps
