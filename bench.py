@@ -31,8 +31,9 @@ IMG, BATCH, LATENT = 64, 128, 100
 # useful conv/linear FLOPs of one DCGAN step at bs 128 (reference formulation)
 GFLOP_PER_STEP_REFERENCE_FORM = 359.0
 # dram__bytes_read.sum + dram__bytes_write.sum of conv_tc_kernel<64,4> on this workload from the committed
-# `ncu --set full` capture (profiles/): 159 MB read + 99 MB written per launch (algorithmic: 67 + 134 MB)
-NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 258.0e6
+# `ncu --set full` capture (profiles/r1_ncu_full_tc_kernels_final.csv): 214 MB read + 104 MB written per launch
+# (algorithmic: 67 MB in + 134 MB out + 0.5 MB weights; the input is re-fetched from DRAM by later phases)
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 318.0e6
 
 
 def parse_args():
