@@ -10,7 +10,7 @@ in DESIGN.md section "Measurement".  Workload = BASELINE.json configs[1]; weak s
                batches; the per-step working set of ~1.5 GB of activations exceeds the 126 MB L2)
   e2e          the same step driven from pinned HOST buffers: H2D copy of images + z every step and a
                D2H read of the two losses (the reference's own per-step .item(), dcgan.py:185-188)
-  roofline     the tcgen05 implicit-GEMM conv kernel (conv_tc_kernel) timed alone with CUDA events
+  roofline     the tcgen05 implicit-GEMM conv kernel of G conv2 timed alone with CUDA events
   cpu_baseline the oracle restatement of the reference step on the host cores (stock torch CPU)
 """
 import argparse
@@ -30,10 +30,10 @@ for p in (ROOT, os.path.join(ROOT, "pytorch-gan_b200")):
 IMG, BATCH, LATENT = 64, 128, 100
 # useful conv/linear FLOPs of one DCGAN step at bs 128 (reference formulation)
 GFLOP_PER_STEP_REFERENCE_FORM = 359.0
-# dram__bytes_read.sum + dram__bytes_write.sum of conv_tc_kernel<64,4> on this workload from the committed
-# `ncu --set full` capture (profiles/r1_ncu_full_tc_kernels_final.csv): 214 MB read + 104 MB written per launch
-# (algorithmic: 67 MB in + 134 MB out + 0.5 MB weights; the input is re-fetched from DRAM by later phases)
-NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 318.0e6
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel on this workload, from the committed
+# `ncu --set full` capture under profiles/ (None until the capture of the current kernel is in; the per-phase
+# predecessor conv_tc_kernel<64,4> moved 214 MB read + 104 MB written for 67 MB in + 134 MB out + 0.5 MB weights)
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = None
 
 
 def parse_args():
@@ -308,7 +308,7 @@ def run_ours(args):
     conv = time_conv_kernel(torch)
     roofline = None
     if conv is not None:
-        roofline = {"kernel": "conv_tc_kernel<64,4> (Upsample x2 + Conv 128->64 3x3 fprop, folded)",
+        roofline = {"kernel": "conv_tc_up2_allphase_kernel (Upsample x2 + Conv 128->64 3x3 fprop, folded, 4 TMEM accumulators)",
                     "bound": "tensor", "achieved": conv["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": conv["tflops"] / tf32_peak, "peak_source": peak_src + ", TF32 = bf16/2",
                     "ms_per_launch": conv["ms"], "algorithmic_gbs": conv["gbs"], "hbm_peak_gbs": hbm_peak,

@@ -340,6 +340,260 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) TC_TRACE(42);
 }
 
+// ---- all-phase kernel for the folded Upsample(2x)+Conv3x3 forward -------------------------------------------
+// The four output phases of the fold read 2x2 windows of the SAME nine shifted input tiles (dh, dw in {-1,0,1}).  The
+// per-phase kernel above fetches 16 A boxes per k-chunk; this one fetches the 9 distinct ones once and feeds each to
+// every phase that uses it (1, 2 or 4 of the four TMEM accumulators; the centre shift is fetched twice so that a stage
+// holds at most two B boxes and three stages fit): operand ingest per MMA drops from 24 KB to 18 KB,
+// which is what bounds the per-phase kernel.  BN = 64: 4 accumulators x 64 columns = 256 TMEM
+// columns, two CTAs per SM still fit (512 columns, 2 x 97 KB of shared memory).
+constexpr int MP_BN = 64;
+constexpr int MP_STAGES = 3;
+constexpr int MP_B_BYTES = MP_BN * TC_BK * 4;
+constexpr int MP_MAX_USES = 2;  // B boxes per stage; the centre shift (used by all four phases) takes two stages
+constexpr int MP_STEPS = 10;
+constexpr int MP_STAGE_BYTES = TC_A_BYTES + MP_MAX_USES * MP_B_BYTES;
+
+struct MpStep {
+  int8_t dw, dh, nb, pad_;
+  int8_t acc[MP_MAX_USES];  // accumulator (= output phase) of each use
+  int8_t bt[MP_MAX_USES];   // tap block of each use in the packed weight matrix
+};
+
+struct MpParams {
+  MpStep steps[MP_STEPS];
+  int32_t kout_total, kchunks, bw_log2, bh_log2, tiles_w, tiles_h, N, Ho, Wo;
+  int32_t out_dc[4], out_da[4];
+  int32_t ldk;
+  const float *bias;
+  const float *chan_scale;
+  double *stats;
+  int32_t stats_groups, stats_per_sample, act;
+  float slope;
+  int32_t rtf;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const __grid_constant__ CUtensorMap tmY, const __grid_constant__ MpParams p) {
+  constexpr int BN = MP_BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + MP_STAGES * MP_STAGE_BYTES);
+  uint64_t *empty = full + MP_STAGES;
+  uint64_t *tmem_full = empty + MP_STAGES;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+  float *red = reinterpret_cast<float *>(tmem_ptr + 2);  // [4][BN][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = blockIdx.y;
+  const int BW = 1 << p.bw_log2, BH = 1 << p.bh_log2;
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2;
+  const int n0 = tn * (TC_BM >> (p.bw_log2 + p.bh_log2));
+  const int iters = MP_STEPS * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < MP_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<4 * BN>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: step-major, k-chunk-minor =====
+      int stage = 0, step = 0, kc = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t *sa = smem + stage * MP_STAGE_BYTES;
+        const MpStep sp = p.steps[step];
+        mbar_arrive_expect_tx(&full[stage], TC_A_BYTES + sp.nb * MP_B_BYTES);
+        tma_load_5d(sa, &tmA, &full[stage], kc * TC_BK, w0 + sp.dw, 0, h0 + sp.dh, n0);
+#pragma unroll 1
+        for (int u = 0; u < sp.nb; ++u)
+          tma_load_2d(sa + TC_A_BYTES + u * MP_B_BYTES, &tmB, &full[stage], kc * TC_BK,
+                      sp.bt[u] * p.kout_total + ntile * BN);
+        if (++kc == p.kchunks) {
+          kc = 0;
+          ++step;
+        }
+        if (++stage == MP_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: one A box feeds every phase that reads this shift =====
+      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN, 0, 0);
+      int stage = 0, step = 0, kc = 0;
+      uint32_t phase = 0, touched = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const MpStep sp = p.steps[step];
+        const uint32_t sa = smem_u32(smem + stage * MP_STAGE_BYTES);
+#pragma unroll 1
+        for (int u = 0; u < sp.nb; ++u) {
+          const uint32_t sb = sa + TC_A_BYTES + u * MP_B_BYTES;
+          const uint32_t acc = (uint32_t)sp.acc[u];
+          const uint32_t fresh = ((touched >> acc) & 1u) ^ 1u;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+            uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+            umma_tf32(tmem + acc * BN, da, db, idesc, (fresh && k == 0) ? 0u : 1u);
+          }
+          touched |= 1u << acc;
+        }
+        umma_commit(&empty[stage]);
+        if (++kc == p.kchunks) {
+          kc = 0;
+          ++step;
+        }
+        if (++stage == MP_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: one accumulator (= output phase) at a time through three 32 KB staging buffers, so the TMA
+    // store of phase j overlaps the TMEM read-out of phase j+1 =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int lw = m & (BW - 1);
+    const int lh = (m >> p.bw_log2) & (BH - 1);
+    const int ln = m >> (p.bw_log2 + p.bh_log2);
+    const int ow = w0 + lw, oh = h0 + lh, on = n0 + ln;
+    const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
+    const float *cs = p.chan_scale ? p.chan_scale + (int64_t)on * p.ldk + ntile * BN : nullptr;
+    const int act = p.act, rtf = p.rtf;
+    const float slope = p.slope;
+    float st1[BN / 32], st2[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) st1[i] = st2[i] = 0.f;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      uint8_t *buf = smem + (j % 3) * (2 * TC_A_BYTES);
+      if (j == 3) {  // buffer 0 is reused: its store must have finished reading shared memory
+        if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN + c), v);
+        if (p.bias) {
+          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + ntile * BN + c);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float4 b = __ldg(b4 + e);
+            v[4 * e] += b.x; v[4 * e + 1] += b.y; v[4 * e + 2] += b.z; v[4 * e + 3] += b.w;
+          }
+        }
+        if (act == B200GAN_ACT_LRELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+        } else if (act == B200GAN_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (act == B200GAN_ACT_TANH) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = tanhf(v[e]);
+        } else if (act == B200GAN_ACT_SIGMOID) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
+        }
+        if (cs && valid) {
+          const float4 *s4 = reinterpret_cast<const float4 *>(cs + c);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float4 b = __ldg(s4 + e);
+            v[4 * e] *= b.x; v[4 * e + 1] *= b.y; v[4 * e + 2] *= b.z; v[4 * e + 3] *= b.w;
+          }
+        }
+        if (rtf) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
+        }
+        {
+          uint8_t *row = buf + (c >> 5) * TC_A_BYTES + m * 128;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            *reinterpret_cast<float4 *>(row + ((e ^ (m & 7)) << 4)) =
+                make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+        if (p.stats) {
+          float s2[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            v[e] = valid ? v[e] : 0.f;
+            s2[e] = v[e] * v[e];
+          }
+          st1[c >> 5] += warp_colsum32(v, lane);
+          st2[c >> 5] += warp_colsum32(s2, lane);
+        }
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+#pragma unroll
+        for (int c = 0; c < BN; c += 32)
+          tma_store_5d(&tmY, buf + (c >> 5) * TC_A_BYTES, p.out_dc[j] + ntile * BN + c, w0, p.out_da[j], h0, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (p.stats) {
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        red[(q * BN + i * 32 + lane) * 2 + 0] = st1[i];
+        red[(q * BN + i * 32 + lane) * 2 + 1] = st2[i];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;
+      if (e < BN) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          a += red[(qq * BN + e) * 2 + 0];
+          b += red[(qq * BN + e) * 2 + 1];
+        }
+        const int gidx = (p.stats_per_sample ? n0 * p.ldk : 0) + ntile * BN + e;
+        atomicAdd(p.stats + gidx, (double)a);
+        atomicAdd(p.stats + p.stats_groups + gidx, (double)b);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<4 * BN>(tmem);
+  }
+}
+
 // ---- host ----------------------------------------------------------------------------------------
 static int ilog2_ceil(int v) {
   int l = 0;
@@ -500,6 +754,95 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   return launch_tc<32, 4>(tmA, tmB, tmY, p, grid, st);
 }
 
+// Folded Upsample(2x)+Conv3x3 forward with all four phases in one CTA (conv_tc_up2_allphase_kernel).
+// x: [N][H][W][C]; y: [N][2H][2W][K] seen through the phase view; packed: [ph][tp][K][C] (B200GAN_PACK_TC_FPROP_UP2).
+static int run_up2_allphase(const float *x, int N, int H, int W, int C, const float *packed, int K,
+                            const b200gan_epilogue *ep, float *y, cudaStream_t st) {
+  MpParams p;
+  memset(&p, 0, sizeof(p));
+  int ns = 0;
+  for (int dh = -1; dh <= 1; ++dh)
+    for (int dw = -1; dw <= 1; ++dw) {
+      // phase (a,b) reads shift (dh,dw) through its tap (dr,ds) = (dh-a+1, dw-b+1) when both are in {0,1}
+      MpStep *s = nullptr;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int dr = dh - a + 1, ds = dw - b + 1;
+          if (dr < 0 || dr > 1 || ds < 0 || ds > 1) continue;
+          if (!s || s->nb == MP_MAX_USES) {  // new stage (the centre shift needs two)
+            s = &p.steps[ns++];
+            s->dw = (int8_t)dw;
+            s->dh = (int8_t)dh;
+          }
+          const int ph = a * 2 + b;
+          s->acc[s->nb] = (int8_t)ph;
+          s->bt[s->nb] = (int8_t)(ph * 4 + dr * 2 + ds);
+          ++s->nb;
+        }
+    }
+  if (ns != MP_STEPS) B2_UNSUPPORTED("internal: all-phase step list");
+  p.kout_total = K;
+  p.kchunks = C / TC_BK;
+  int bwl = ilog2_ceil(W);
+  if (bwl > 7) bwl = 7;
+  int bhl = ilog2_ceil(H);
+  if (bhl > 7 - bwl) bhl = 7 - bwl;
+  const int BW = 1 << bwl, BH = 1 << bhl, BNn = TC_BM / (BW * BH);
+  p.bw_log2 = bwl;
+  p.bh_log2 = bhl;
+  p.tiles_w = ceil_div(W, BW);
+  p.tiles_h = ceil_div(H, BH);
+  p.N = N;
+  p.Ho = H;
+  p.Wo = W;
+  for (int ph = 0; ph < 4; ++ph) {
+    p.out_dc[ph] = (ph & 1) * K;
+    p.out_da[ph] = ph >> 1;
+  }
+  p.ldk = K;
+  p.bias = ep ? ep->bias : nullptr;
+  p.chan_scale = ep ? ep->chan_scale : nullptr;
+  p.stats = ep ? ep->stats : nullptr;
+  p.stats_per_sample = ep ? ep->stats_per_sample : 0;
+  p.stats_groups = p.stats_per_sample ? N * K : K;
+  if (p.stats && p.stats_per_sample && BNn != 1)
+    B2_UNSUPPORTED("tcgen05 fprop: per-sample statistics need one image per tile (H*W >= 128 per phase)");
+  p.act = ep ? ep->act : 0;
+  p.slope = ep ? ep->slope : 0.f;
+  p.rtf = ep ? ep->round_tf32 : 0;
+  B2_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)packed % 16 == 0) && ((uintptr_t)y % 16 == 0),
+               "tcgen05 conv: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB, tmY;
+  uint32_t box[5] = {TC_BK, (uint32_t)BW, 1, (uint32_t)BH, (uint32_t)BNn};
+  {
+    const uint64_t L = (uint64_t)K;
+    uint64_t dims[5] = {2 * L, (uint64_t)W, 2, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[4] = {2 * L * 4, (uint64_t)2 * W * L * 4, (uint64_t)4 * W * L * 4, (uint64_t)4 * H * W * L * 4};
+    if (int e = make_tmap_f32(&tmY, y, 5, dims, strides, box)) return e;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, 1, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[4] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+    if (int e = make_tmap_f32(&tmA, x, 5, dims, strides, box)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)16 * K};
+    uint64_t strides[1] = {(uint64_t)C * 4};
+    uint32_t bbox[2] = {TC_BK, (uint32_t)MP_BN};
+    if (int e = make_tmap_f32(&tmB, packed, 2, dims, strides, bbox)) return e;
+  }
+  constexpr int SMEM = MP_STAGES * MP_STAGE_BYTES + 1024 + 256 + 4 * MP_BN * 2 * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CUDA(cudaFuncSetAttribute(conv_tc_up2_allphase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(K / MP_BN), 1);
+  conv_tc_up2_allphase_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, tmY, p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
 static inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 // gather form.  in: [N][Hi][Wi][Cc]; out: [N][Po][Qo][Kout]; B: [R*S][Kout][Cc]
@@ -578,6 +921,10 @@ int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float
   if (ep) e2 = *ep;
   const b200gan_epilogue *e = ep ? &e2 : nullptr;
   if (g->up == 2) {
+    // 64-wide output tiles: all four phases in one CTA (9 operand fetches per k-chunk instead of 16)
+    static const bool allphase = !(getenv("B200GAN_UP2_ALLPHASE") && atoi(getenv("B200GAN_UP2_ALLPHASE")) == 0);
+    if (allphase && g->K % 128 != 0 && g->K % 64 == 0)
+      return run_up2_allphase(x, g->N, g->H, g->W, g->C, packed, g->K, e, y, st);
     // phase (a,b): out[2i+a][2j+b] = sum_{dr,ds} x[i+a-1+dr][j+b-1+ds] * Wf[a][b][dr][ds]
     TcTap taps[TC_MAX_TAPS];
     memset(taps, 0, sizeof(taps));

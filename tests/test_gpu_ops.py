@@ -146,6 +146,56 @@ def test_upsample_conv_folded(cin, cout, h, w, n):
     assert rel_err(ours[1].bias.grad, ref[1].bias.grad) < TOL
 
 
+@pytest.mark.parametrize("slope", [1.0, 0.2])
+@pytest.mark.parametrize("norm,cin,cout,h,w,n", [("bn", 64, 64, 6, 5, 3), ("bn", 128, 64, 16, 16, 2),
+                                                 ("in", 32, 64, 16, 8, 2), ("bn", 32, 192, 4, 4, 5)])
+def test_upsample_conv_norm_act_all_phase_kernel(norm, cin, cout, h, w, n, slope):
+    """Upsample -> Conv3x3 -> BatchNorm/InstanceNorm -> LeakyReLU (dcgan.py:54-57; cyclegan/models.py:73-78).  With
+    64 (mod 128) output channels the forward runs in the all-phase tcgen05 kernel: 9 shifted operand tiles feed four
+    TMEM accumulators, the norm statistics are summed over the four phases in the epilogue.  Ragged and < 128-pixel
+    maps exercise TMA clipping; the InstanceNorm case needs one image per tile."""
+    bnn = _mods()
+    torch.manual_seed(11)
+    mk = (lambda nn_: nn_.BatchNorm2d(cout, 0.8)) if norm == "bn" else (lambda nn_: nn_.InstanceNorm2d(cout))
+    ref = torch.nn.Sequential(torch.nn.Upsample(scale_factor=2), torch.nn.Conv2d(cin, cout, 3, 1, 1), mk(torch.nn),
+                              torch.nn.LeakyReLU(slope, inplace=True)).cuda()
+    ours = bnn.Sequential(bnn.Upsample(scale_factor=2), bnn.Conv2d(cin, cout, 3, 1, 1), mk(bnn),
+                          bnn.LeakyReLU(slope, inplace=True)).cuda()
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(n, cin, h, w, device="cuda")
+    gy = torch.randn(n, cout, 2 * h, 2 * w, device="cuda")
+
+    def run(model, tf32):
+        torch.backends.cudnn.allow_tf32 = tf32
+        model.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        y = model(xi)
+        y.backward(gy)
+        torch.backends.cudnn.allow_tf32 = False
+        return y.detach(), xi.grad, model[1].weight.grad.clone()
+
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    yr, gxr, gwr = run(ref, False)
+    rm, rv = ref[2].running_mean, ref[2].running_var
+    if norm == "bn":
+        rm, rv = rm.clone(), rv.clone()
+    yo, gxo, gwo = run(ours, False)
+    assert rel_err(yo, yr) < TOL
+    if norm == "bn":
+        assert rel_err(ours[2].running_mean, rm) < TOL
+        assert rel_err(ours[2].running_var, rv) < TOL
+    # Backward.  slope 1.0 (no kink) isolates the kernels: 2e-3.  With slope 0.2 the TF32 forward leaves a few
+    # pre-activations with |norm(z)| < 5e-4 on the other side of the LeakyReLU kink and every such flip changes dz by
+    # 0.8 * dy at that element: an fp32 CPU emulation with truncated operands (tools/tf32_kink_emulation.py) loses
+    # 3.5e-3 / 1.3e-2 on the first two cases, a property of TF32 convolutions (stock cuDNN-TF32 loses the same where it
+    # picks a TF32 kernel).  Bound there: 2e-2, or 1.5x what stock torch TF32 loses if that is more.
+    ref.load_state_dict(sd)
+    _, gxt, gwt = run(ref, True)
+    floor = 2 * TOL if slope == 1.0 else 20 * TOL
+    assert rel_err(gxo, gxr) < max(floor, 1.5 * rel_err(gxt, gxr))
+    assert rel_err(gwo, gwr) < max(floor, 1.5 * rel_err(gwt, gwr))
+
+
 def test_padded_convs_in_sequential():
     """ReflectionPad2d(3) -> Conv7x7 (cyclegan/models.py:49-50) and Upsample -> ZeroPad2d((1,0,1,0)) ->
     Conv4x4 p1 -> Tanh (pix2pix/models.py:76-81)."""
