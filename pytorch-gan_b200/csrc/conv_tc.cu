@@ -371,6 +371,7 @@ struct MpParams {
   int32_t stats_groups, stats_per_sample, act;
   float slope;
   int32_t rtf;
+  long long *trace;  // bring-up: per-CTA clock64 timeline (64 slots per CTA) or nullptr
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -396,6 +397,7 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2;
   const int n0 = tn * (TC_BM >> (p.bw_log2 + p.bh_log2));
   const int iters = MP_STEPS * p.kchunks;
+  if (threadIdx.x == 0) TC_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -413,6 +415,7 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 0) TC_TRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -423,6 +426,8 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t *sa = smem + stage * MP_STAGE_BYTES;
         const MpStep sp = p.steps[step];
+        if (it < 16) TC_TRACE(2 + it);
+        if (it == iters - 1) TC_TRACE(18);
         mbar_arrive_expect_tx(&full[stage], TC_A_BYTES + sp.nb * MP_B_BYTES);
         tma_load_5d(sa, &tmA, &full[stage], kc * TC_BK, w0 + sp.dw, 0, h0 + sp.dh, n0);
 #pragma unroll 1
@@ -448,6 +453,8 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       for (int it = 0; it < iters; ++it) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (it < 16) TC_TRACE(20 + it);
+        if (it == iters - 1) TC_TRACE(36);
         const MpStep sp = p.steps[step];
         const uint32_t sa = smem_u32(smem + stage * MP_STAGE_BYTES);
 #pragma unroll 1
@@ -493,6 +500,7 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     for (int i = 0; i < BN / 32; ++i) st1[i] = st2[i] = 0.f;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TC_TRACE(40);
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
       uint8_t *buf = smem + (j % 3) * (2 * TC_A_BYTES);
@@ -500,6 +508,7 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      if (threadIdx.x == 64) TC_TRACE(48 + 3 * j);
 #pragma unroll
       for (int c = 0; c < BN; c += 32) {
         float v[32];
@@ -555,16 +564,22 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           st2[c >> 5] += warp_colsum32(s2, lane);
         }
       }
+      if (threadIdx.x == 64) TC_TRACE(49 + 3 * j);
       fence_proxy_async();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
+        TC_TRACE(50 + 3 * j);
 #pragma unroll
         for (int c = 0; c < BN; c += 32)
           tma_store_5d(&tmY, buf + (c >> 5) * TC_A_BYTES, p.out_dc[j] + ntile * BN + c, w0, p.out_da[j], h0, n0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (threadIdx.x == 64) {
+      TC_TRACE(43);
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      TC_TRACE(41);
+    }
     if (p.stats) {
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
@@ -592,6 +607,7 @@ conv_tc_up2_allphase_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     __syncwarp();
     tmem_dealloc<4 * BN>(tmem);
   }
+  if (threadIdx.x == 0) TC_TRACE(42);
 }
 
 // ---- host ----------------------------------------------------------------------------------------
@@ -810,6 +826,8 @@ static int run_up2_allphase(const float *x, int N, int H, int W, int C, const fl
   p.act = ep ? ep->act : 0;
   p.slope = ep ? ep->slope : 0.f;
   p.rtf = ep ? ep->round_tf32 : 0;
+  p.trace = nullptr;
+  if (const char *tv = getenv("B200GAN_TC_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(tv, nullptr, 0));
   B2_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)packed % 16 == 0) && ((uintptr_t)y % 16 == 0),
                "tcgen05 conv: pointers must be 16-byte aligned");
   CUtensorMap tmA, tmB, tmY;
