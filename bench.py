@@ -30,10 +30,11 @@ for p in (ROOT, os.path.join(ROOT, "pytorch-gan_b200")):
 IMG, BATCH, LATENT = 64, 128, 100
 # useful conv/linear FLOPs of one DCGAN step at bs 128 (reference formulation)
 GFLOP_PER_STEP_REFERENCE_FORM = 359.0
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel on this workload, from the committed
-# `ncu --set full` capture under profiles/ (None until the capture of the current kernel is in; the per-phase
-# predecessor conv_tc_kernel<64,4> moved 214 MB read + 104 MB written for 67 MB in + 134 MB out + 0.5 MB weights)
-NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (conv_tc_up2_allphase_kernel) on this
+# workload, from the committed `ncu --set full` capture profiles/r1_ncu_full_up2_allphase_kernel.csv: 68.1 MB read +
+# 78.4 MB written (algorithmic: 67 MB in + 134 MB out + 0.5 MB weights; part of the output is still in the 126 MB L2
+# when the kernel ends; the per-phase predecessor conv_tc_kernel<64,4> moved 214 + 104 MB)
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 146.5e6
 
 
 def parse_args():
