@@ -621,11 +621,8 @@ template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmY, const TcParams &p, dim3 grid,
                      cudaStream_t st) {
   constexpr int SMEM = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + 4 * BN * 2 * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  if (int e = ensure_dynamic_smem(conv_tc_kernel<BN, STAGES>, SMEM, attr_done)) return e;
   conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, tmY, p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
@@ -850,11 +847,8 @@ static int run_up2_allphase(const float *x, int N, int H, int W, int C, const fl
     if (int e = make_tmap_f32(&tmB, packed, 2, dims, strides, bbox)) return e;
   }
   constexpr int SMEM = MP_STAGES * MP_STAGE_BYTES + 1024 + 256 + 4 * MP_BN * 2 * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2_CUDA(cudaFuncSetAttribute(conv_tc_up2_allphase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  if (int e = ensure_dynamic_smem(conv_tc_up2_allphase_kernel, SMEM, attr_done)) return e;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(K / MP_BN), 1);
   conv_tc_up2_allphase_kernel<<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, tmY, p);
   B2_LAUNCH_CHECK();

@@ -3,6 +3,7 @@
 // side tensor-map encoder (driver entry point fetched through the runtime, no -lcuda needed).
 #pragma once
 #include <cuda.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace b200gan {
@@ -115,6 +116,22 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, const vo
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: opt-in dynamic shared memory.  cudaFuncSetAttribute is per device, so remember which device ordinals already
+// have it (one bit each); safe to call from several host threads and inside stream capture (it is not a stream op).
+// ---------------------------------------------------------------------------------------------
+template <class Kernel>
+static inline int ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<uint64_t> &done) {
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    B2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
+  }
+  return B200GAN_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

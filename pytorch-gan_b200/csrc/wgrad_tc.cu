@@ -310,11 +310,8 @@ template <int NB, int STAGES>
 static int launch_wg(const CUtensorMap &tmX, const CUtensorMap &tmY, const CUtensorMap &tmP, const WgParams &p, dim3 grid,
                      cudaStream_t st) {
   constexpr int SMEM = STAGES * (4 + NB / 32) * WG_CHUNK_BYTES + 1024 + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  if (int e = ensure_dynamic_smem(wgrad_tc_kernel<NB, STAGES>, SMEM, attr_done)) return e;
   wgrad_tc_kernel<NB, STAGES><<<grid, WG_THREADS, SMEM, st>>>(tmX, tmY, tmP, p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
