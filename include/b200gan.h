@@ -227,10 +227,12 @@ int b200gan_gp_mlp_fwd_bwd(const b200gan_gp_mlp_desc *d, const float *xi, const 
 
 /* ---- flat-buffer Adam (torch.optim.Adam semantics: dcgan.py:134-135) --------------------- */
 /* p -= lr * mhat / (sqrt(vhat) + eps), bias-corrected with the step count read from the
- * device (step[0] is incremented by the kernel -> CUDA-graph capturable).
+ * device (step[0] is incremented by the kernel -> CUDA-graph capturable).  lr, betas and eps
+ * are doubles like torch's Python-side hyper-parameters: torch forms 1 - beta, 1 - beta^t and
+ * lr / (1 - beta1^t) in double and casts them to fp32 where they meet a tensor.
  * grad_scale multiplies g first (1/world_size after an all-reduce sum). */
-int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
-                      float beta1, float beta2, float eps, float grad_scale, float *step,
+int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, double lr,
+                      double beta1, double beta2, double eps, float grad_scale, float *step,
                       void *stream);
 
 #ifdef __cplusplus

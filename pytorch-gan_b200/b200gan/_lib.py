@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200gan.so")
 
-c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+c_i32, c_i64, c_f32, c_f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 c_vp, c_sz = ctypes.c_void_p, ctypes.c_size_t
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -71,7 +71,7 @@ SIGNATURES = {
     "b200gan_act_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_f32, c_i64, c_i32, c_i64, c_vp, c_vp]),
     "b200gan_gp_mlp_workspace_floats": (c_sz, [_P(GpMlpDesc)]),
     "b200gan_gp_mlp_fwd_bwd": (c_i32, [_P(GpMlpDesc)] + [c_vp] * 12),
-    "b200gan_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp]),
+    "b200gan_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f32, c_vp, c_vp]),
 }
 
 _lib = None

@@ -210,25 +210,28 @@ bias_grad_kernel(const float *__restrict__ dy, const float *__restrict__ y, cons
 }
 
 // ---- Adam ---------------------------------------------------------------------------------------------
-// torch.optim.Adam (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
-// p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  Step count lives on the device.
+// torch.optim.Adam (no amsgrad, no weight decay), arithmetic of _single_tensor_adam: the hyper-parameters, the bias
+// corrections 1 - beta^t and the step size lr / (1 - beta1^t) are Python doubles that are cast to fp32 only where they
+// meet a tensor -- (float)(1 - 0.999) is not 1.f - 0.999f (1.3e-5 apart), so they arrive here as doubles too.
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= step_size * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// The step count lives on the device (CUDA-graph capturable).
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
-                            float *__restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float *__restrict__ v, int64_t n, double lr, double b1, double b2, double eps,
                             float gscale, const float *__restrict__ step) {
-  float t = *step + 1.f;
-  float bc1 = 1.f - powf(b1, t);
-  float bc2 = 1.f - powf(b2, t);
-  float step_size = lr / bc1;
-  float bc2_sqrt = sqrtf(bc2);
+  const double t = (double)*step + 1.0;
+  const float neg_step_size = (float)(-(lr / (1.0 - pow(b1, t))));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(b2, t));
+  const float b1f = (float)b1, omb1 = (float)(1.0 - b1), b2f = (float)b2, omb2 = (float)(1.0 - b2);
+  const float epsf = (float)eps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * gscale;
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float mi = b1f * m[i] + omb1 * gi;
+    float vi = b2f * v[i] + omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= step_size * (mi / denom);
+    float denom = sqrtf(vi) / bc2_sqrt + epsf;
+    p[i] += neg_step_size * (mi / denom);
   }
 }
 __global__ void adam_step_inc_kernel(float *step) { *step += 1.f; }
@@ -321,8 +324,8 @@ extern "C" int b200gan_epilogue_bwd(const float *dy, const float *y, const float
   return B200GAN_OK;
 }
 
-extern "C" int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr,
-                                 float beta1, float beta2, float eps, float grad_scale, float *step,
+extern "C" int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, double lr,
+                                 double beta1, double beta2, double eps, float grad_scale, float *step,
                                  void *stream) {
   B2_CHECK_ARG(p && g && m && v && step, "adam_step: null pointer");
   if (n > 0) {
