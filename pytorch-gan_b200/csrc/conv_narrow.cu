@@ -45,6 +45,9 @@ bool narrow_gather_ok(int C, int K, int R, int S, int stride, int pad_mode, int 
   if (pad_mode != B200GAN_PAD_ZERO || up != 1 || (stride != 1 && stride != 2)) return false;
   if (C < 1 || K < 1 || C > 64 || K > 64) return false;
   if ((int64_t)R * S * C * K * 4 > 96 * 1024) return false;
+  // one thread per pixel reading > 64 B of channels: a warp's 16-byte loads scatter over 32 lines and the L1 becomes
+  // the bottleneck (estimate for the 64 -> 1 output conv: 2.5x slower than the lane-per-channel kernels)
+  if (K < 4 && C > 16) return false;
   return aligned16(x) && aligned16(wp) && aligned16(y);
 }
 
@@ -70,9 +73,12 @@ int narrow_gather(int N, int H, int W, int C, int P, int Q, int K, int R, int S,
   return B200GAN_OK;
 }
 
-bool narrow_wgrad_ok(int Cg, int Cd, int R, int S, int pad_mode, int up, const void *xg, const void *dn) {
+bool narrow_wgrad_ok(int64_t gathered_floats, int Cg, int Cd, int R, int S, int pad_mode, int up, const void *xg,
+                     const void *dn) {
   if (pad_mode != B200GAN_PAD_ZERO || up != 1) return false;
   if (Cg < 1 || Cd < 1 || Cg > 64 || Cd > 64 || R * S > 49) return false;
+  // every tap is its own set of threads, so the gathered tensor is read R*S times: it has to sit in L2
+  if (gathered_floats * 4 > (int64_t)32 << 20) return false;
   return aligned16(xg) && aligned16(dn);
 }
 

@@ -19,7 +19,8 @@ bool narrow_gather_ok(int C, int K, int R, int S, int stride, int pad_mode, int 
                       const void *y);
 int narrow_gather(int N, int H, int W, int C, int P, int Q, int K, int R, int S, int stride, int pad_t, int pad_l, int mode,
                   const b200gan_epilogue *ep, const float *x, const float *wp, float *y, cudaStream_t st);
-bool narrow_wgrad_ok(int Cg, int Cd, int R, int S, int pad_mode, int up, const void *xg, const void *dn);
+bool narrow_wgrad_ok(int64_t gathered_floats, int Cg, int Cd, int R, int S, int pad_mode, int up, const void *xg,
+                     const void *dn);
 int narrow_wgrad(int N, int H, int W, int Cg, int P, int Q, int Cd, int R, int S, int stride, int pad_t, int pad_l,
                  const float *xg, const float *dn, float *dw, cudaStream_t st);
 
@@ -878,7 +879,7 @@ int simt_wgrad(int N, int H, int W, int Cg, int P, int Q, int Cd, int R, int S, 
   int Ktot = R * S * Cg;
   B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)Ktot * Cd * sizeof(float), st));
   if (M == 0) return B200GAN_OK;
-  if (narrow_enabled() && narrow_wgrad_ok(Cg, Cd, R, S, pad_mode, up, xg, dn))
+  if (narrow_enabled() && narrow_wgrad_ok((int64_t)N * H * W * Cg, Cg, Cd, R, S, pad_mode, up, xg, dn))
     return narrow_wgrad(N, H, W, Cg, P, Q, Cd, R, S, stride, pad_t, pad_l, xg, dn, dw, st);
   if (Cd == 1 && R == 3 && S == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && up == 1 && pad_mode == B200GAN_PAD_ZERO &&
       P == H && Q == W && Cg % 4 == 0 && Cg >= 16 && Cg <= 128 && ((uintptr_t)xg % 16 == 0)) {

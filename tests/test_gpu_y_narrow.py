@@ -17,7 +17,7 @@ CASES = [  # cin, cout, k, stride, pad, H, W, N
     (1, 16, 3, 2, 1, 64, 64, 8),     # dcgan D conv1
     (16, 32, 3, 2, 1, 32, 32, 8),    # D conv2
     (32, 64, 3, 2, 1, 16, 16, 8),    # D conv3
-    (64, 1, 3, 1, 1, 64, 64, 4),     # G output conv
+    (1, 64, 3, 1, 1, 32, 32, 4),     # one input channel, stride 1 (the dgrad direction of the G output conv)
     (16, 32, 3, 2, 1, 11, 9, 3),     # ragged parity classes
     (8, 16, 4, 2, 1, 12, 10, 2),
 ]
