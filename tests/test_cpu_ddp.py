@@ -46,7 +46,7 @@ def _worker(rank, world, port, out):
 
 def test_grad_reducer_world_size_2_matches_full_batch():
     world, port = 2, _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # no fork() of this multi-threaded process
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     net = _model()
