@@ -319,7 +319,7 @@ def run_ours(args):
                     "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (rank 0); the scaling runs skip it
         ips, spstep, threads, batch = cpu_step_throughput(2, 1, budget_s=25.0)
         cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"2 steps on {batch} of the {BATCH} images per step after 1 warm-up, oracle port of "
