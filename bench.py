@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "stock", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager step loop (debugging)")
     return ap.parse_args()
@@ -221,8 +221,14 @@ def run_ours(args):
     b200gan.load_library()
 
     torch.manual_seed(0)  # identical init on every rank
-    g = zoo.DCGANGenerator(IMG).to(dev)
-    d = zoo.DCGANDiscriminator(IMG).to(dev)
+    stock = args.impl == "stock"
+    ns = zoo.namespace(stock=stock)
+    if stock:  # the reference's own GPU path: stock torch.nn on cuDNN/cuBLAS with TF32 allowed (torch's conv default)
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.benchmark = True
+    g = zoo.DCGANGenerator(IMG, nn=ns).to(dev)
+    d = zoo.DCGANDiscriminator(IMG, nn=ns).to(dev)
     g.apply(zoo.weights_init_normal)
     d.apply(zoo.weights_init_normal)
     opt_g = torch.optim.Adam(g.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=True)
@@ -306,7 +312,7 @@ def run_ours(args):
 
     hbm_peak, bf16_peak, peak_src = measured_peaks()
     tf32_peak = bf16_peak / 2.0  # kind::tf32 issues at half the kind::f16 rate (guide: 1.13 vs 2.25 PF nominal)
-    conv = time_conv_kernel(torch)
+    conv = None if stock else time_conv_kernel(torch)
     roofline = None
     if conv is not None:
         roofline = {"kernel": "conv_tc_up2_allphase_kernel (Upsample x2 + Conv 128->64 3x3 fprop, folded, 4 TMEM accumulators)",
@@ -328,6 +334,7 @@ def run_ours(args):
     h2d = sum(t_.numel() * 4 for t_ in (host_imgs[0], host_z[0]))
     step_ms = ms / args.steps
     line = {
+        "impl": args.impl,
         "metric": "DCGAN 64x64 images/sec (full G+D step)",
         "value": BATCH * world * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",

@@ -184,6 +184,34 @@ int b200gan_norm_bwd(const b200gan_norm_desc *d, const float *dy, const float *x
                      const float *mean_rstd, const float *gamma, double *sums, float *dx,
                      float *dgamma_dbeta, void *stream);
 
+/* ---- Generator tail: BatchNorm2d -> LeakyReLU/ReLU -> Conv2d(C, K<=3, 3, 1, 1) -> Tanh, fused -------------- */
+/* Replaces the module run dcgan.py:60-63
+ *     nn.BatchNorm2d(64, 0.8), nn.LeakyReLU(0.2, inplace=True), nn.Conv2d(64, opt.channels, 3, stride=1, padding=1), nn.Tanh()
+ * acting on `a`, the raw output of the preceding convolution: the normalised/activated tensor, its gradient and the
+ * conv's data gradient are never written to memory (csrc/tail.cu).  scale_shift / mean_rstd come from
+ * b200gan_norm_finalize (batch statistics of `a`).  Supported: C in {32, 64, 128}, K in 1..3, W a power of two in
+ * [16, 128], act_mid in {NONE, LRELU, RELU}. */
+typedef struct b200gan_tail_desc {
+  int32_t N, H, W, C; /* a: [N][H][W][C] */
+  int32_t K;          /* conv output channels; the conv is 3x3, stride 1, zero padding 1 */
+  int32_t act_mid;    /* activation between the norm and the conv */
+  float slope;
+  int32_t act_out;    /* activation after the conv (+bias) */
+} b200gan_tail_desc;
+int b200gan_tail_supported(const b200gan_tail_desc *d);
+/* out[N][H][W][K] = act_out(conv3x3(act_mid(a * scale + shift), w) + bias); w: the Conv2d parameter [K][C][3][3].
+ * The convolution runs on tcgen05 (kind::tf32). */
+int b200gan_tail_fprop(const b200gan_tail_desc *d, const float *a, const float *scale_shift, const float *w,
+                       const float *bias, float *out, void *stream);
+/* Backward of the same composite given g = d(loss)/d(conv output before act_out) [N][H][W][K]:
+ *   da[N][H][W][C]  gradient w.r.t. `a` through conv, activation and the training-mode BatchNorm
+ *   dgamma_dbeta[2][C] (may be NULL), dw[K][C][3][3], db[K] (may be NULL) -- all OVERWRITTEN.
+ * workspace: b200gan_tail_bwd_workspace_bytes() bytes, 16-byte aligned (zeroed by the call). */
+size_t b200gan_tail_bwd_workspace_bytes(const b200gan_tail_desc *d);
+int b200gan_tail_bwd(const b200gan_tail_desc *d, const float *a, const float *mean_rstd, const float *scale_shift,
+                     const float *w, const float *g, void *workspace, float *da, float *dgamma_dbeta, float *dw,
+                     float *db, int32_t round_tf32, void *stream);
+
 /* ---- shape / index ops (bit-exact) ---------------------------------------------------- */
 /* NCHW <-> NHWC transposes of a dense fp32 tensor. */
 int b200gan_nchw_to_nhwc(const float *x, float *y, int32_t N, int32_t C, int32_t HW, void *stream);

@@ -42,6 +42,11 @@ class GpMlpDesc(ctypes.Structure):
                 ("lambda_gp", c_f32)]
 
 
+class TailDesc(ctypes.Structure):
+    _fields_ = [("N", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32), ("K", c_i32), ("act_mid", c_i32),
+                ("slope", c_f32), ("act_out", c_i32)]
+
+
 # name -> (restype, argtypes); must list every function declared in include/b200gan.h
 _P = ctypes.POINTER
 SIGNATURES = {
@@ -62,6 +67,10 @@ SIGNATURES = {
     "b200gan_norm_finalize": (c_i32, [_P(NormDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200gan_norm_apply": (c_i32, [_P(NormDesc), c_vp, c_vp, c_vp, c_vp]),
     "b200gan_norm_bwd": (c_i32, [_P(NormDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200gan_tail_supported": (c_i32, [_P(TailDesc)]),
+    "b200gan_tail_fprop": (c_i32, [_P(TailDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200gan_tail_bwd_workspace_bytes": (c_sz, [_P(TailDesc)]),
+    "b200gan_tail_bwd": (c_i32, [_P(TailDesc)] + [c_vp] * 10 + [c_i32, c_vp]),
     "b200gan_nchw_to_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "b200gan_nhwc_to_nchw": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "b200gan_upsample2x_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

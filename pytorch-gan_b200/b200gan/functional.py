@@ -118,6 +118,7 @@ class ConvFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy, *unused):
         x, weight, y, chan_scale = ctx.saved_tensors
         spec, g = ctx.spec, ctx.g
@@ -167,6 +168,7 @@ class NormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         x, y, mean_rstd, gamma = ctx.saved_tensors
         spec = ctx.spec
@@ -184,6 +186,54 @@ class NormFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, None, None
 
 
+@dataclass(frozen=True)
+class TailSpec:
+    eps: float = 1e-5
+    momentum: float = 0.0
+    act_mid: int = ACT_NONE
+    slope: float = 0.0
+    act_out: int = ACT_NONE
+    rtf_dx: bool = False
+
+
+class TailFn(torch.autograd.Function):
+    """Training-mode BatchNorm2d -> LeakyReLU/ReLU -> Conv2d(C, K<=3, 3, 1, 1) [-> Tanh] on the raw output `a` of
+    the preceding conv (dcgan.py:60-63), without materialising the normalised tensor or any gradient of it."""
+
+    @staticmethod
+    def forward(ctx, a, stats, gamma, beta, running_mean, running_var, nbt, weight, bias, spec: TailSpec):
+        ops._require_cuda(a, "tail input")
+        a = _as_cl(a)
+        if stats is None or stats.numel() == 0:
+            stats = ops.norm_stats(a, False)
+        mean_rstd, scale_shift = ops.norm_finalize(
+            tuple(a.shape), stats, None if gamma is None else gamma.detach(), None if beta is None else beta.detach(),
+            running_mean, running_var, nbt, False, spec.eps, spec.momentum, a.device)
+        d = ops.tail_desc(tuple(a.shape), weight.shape[0], spec.act_mid, spec.slope, spec.act_out)
+        w = weight.detach().contiguous()
+        out = ops.tail_fprop(d, a, scale_shift, w, None if bias is None else bias.detach())
+        ctx.spec, ctx.d = spec, d
+        ctx.has_affine, ctx.has_bias = gamma is not None, bias is not None
+        ctx.save_for_backward(a, mean_rstd, scale_shift, weight, out if spec.act_out != ACT_NONE else None)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        a, mean_rstd, scale_shift, weight, out = ctx.saved_tensors
+        spec = ctx.spec
+        dout = _as_cl(dout)
+        g = ops.epilogue_bwd(dout, out, None, spec.act_out, 0.0) if spec.act_out != ACT_NONE else dout
+        need_affine = ctx.has_affine and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        need_bias = ctx.has_bias and ctx.needs_input_grad[8]
+        da, dgb, dw, db = ops.tail_bwd(ctx.d, a, mean_rstd, scale_shift, weight.detach().contiguous(), g, need_affine,
+                                       need_bias, spec.rtf_dx)
+        c = a.shape[1]
+        dgamma = dgb[:c] if need_affine else None
+        dbeta = dgb[c:] if need_affine else None
+        return da, None, dgamma, dbeta, None, None, None, dw, db, None
+
+
 class AffineActFn(torch.autograd.Function):
     """y = act(x * scale[c] + shift[c]) with constant scale/shift: eval-mode BatchNorm2d."""
 
@@ -196,6 +246,7 @@ class AffineActFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         y, scale_shift = ctx.saved_tensors
         dy = _as_cl(dy)
@@ -213,6 +264,7 @@ class ToChannelsLastFn(torch.autograd.Function):
         return ops.to_cl(x)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         return ops.to_nchw(dy)
 
@@ -223,6 +275,7 @@ class ToContiguousFn(torch.autograd.Function):
         return ops.to_nchw(x)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         return _as_cl(dy)
 
@@ -233,6 +286,7 @@ class UpsampleFn(torch.autograd.Function):
         return ops.upsample2x(_as_cl(x))
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         return ops.upsample2x_bwd(_as_cl(dy))
 
@@ -244,6 +298,7 @@ class PadFn(torch.autograd.Function):
         return ops.pad2d(_as_cl(x), pads, mode, round_tf32)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         return ops.pad2d_bwd(_as_cl(dy), ctx.pads, ctx.mode), None, None, None
 
@@ -260,6 +315,7 @@ class ActFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         y, mask = ctx.saved_tensors
         dy = _as_cl(dy)

@@ -248,6 +248,7 @@ class _ConvStep:
         self.act, self.slope, self.dropout2d, self.stats = act, slope, dropout2d, stats
         self.rtf_out = False
         self.rtf_dz = False
+        self.next_norm = None
 
     def tc_like(self):
         if self.pad_mode == PAD_REFLECT and self.up != 1:
@@ -265,6 +266,32 @@ class _NormStep:
 class _LeafStep:
     def __init__(self, mod):
         self.mod = mod
+
+
+class _TailStep:
+    """BatchNorm2d [-> LeakyReLU/ReLU] -> Conv2d(C, K<=3, 3, 1, 1) [-> act]: the fused Generator tail (dcgan.py:60-63).
+    Keeps the two steps it replaces for the cases the fused kernels do not take (eval mode, odd sizes)."""
+
+    def __init__(self, norm_step, conv_step):
+        self.norm_step, self.conv_step = norm_step, conv_step
+
+
+def _uses_batch_stats(norm):
+    return isinstance(norm, _T["InstanceNorm2d"]) or norm.training or norm.running_mean is None
+
+
+def _tail_candidate(ns, cs):
+    if not (isinstance(ns, _NormStep) and isinstance(cs, _ConvStep)):
+        return False
+    norm, conv = ns.norm, cs.conv
+    if not isinstance(norm, _T["BatchNorm2d"]) or ns.act not in (ACT_NONE, ACT_LRELU, ACT_RELU):
+        return False
+    if isinstance(conv, _T["ConvTranspose2d"]) or cs.up != 1 or cs.extra_pads != (0, 0, 0, 0) or cs.pad_mode != PAD_ZERO:
+        return False
+    if cs.dropout2d is not None or cs.stats is not None:
+        return False
+    return (tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (1, 1)
+            and conv.out_channels <= 3 and conv.in_channels in (32, 64, 128))
 
 
 def _is_norm(m):
@@ -300,6 +327,7 @@ def _build_plan(mods):
             if j < n and _is_norm(mods[j]):
                 stats = isinstance(mods[j], _T["InstanceNorm2d"])
             steps.append(_ConvStep(conv, up, extra, mode, act, slope, d2, stats))
+            steps[-1].next_norm = mods[j] if stats is not None else None
             i = j
             continue
         m = mods[i]
@@ -329,7 +357,16 @@ def _build_plan(mods):
             if (k + 1 < len(steps) and isinstance(steps[k + 1], _NormStep) and s.act == ACT_NONE
                     and s.dropout2d is None):
                 steps[k + 1].rtf_dx = True
-    return steps
+    # the Generator tail: norm + narrow 3x3 conv as one fused node
+    fused, k = [], 0
+    while k < len(steps):
+        if k + 1 < len(steps) and _tail_candidate(steps[k], steps[k + 1]):
+            fused.append(_TailStep(steps[k], steps[k + 1]))
+            k += 2
+        else:
+            fused.append(steps[k])
+            k += 1
+    return fused
 
 
 class Sequential(_T["Sequential"]):
@@ -347,21 +384,45 @@ class Sequential(_T["Sequential"]):
             return super().forward(x)
         steps = self._plan()
         if all(isinstance(s, _LeafStep) for s in steps):
-            return super().forward(x)
+            return _T["Sequential"].forward(self, x)
         # Output memory format follows the input's -- the scripts .view() conv outputs only where they are small
         # (dcgan.py:96: [N,128,4,4] -> [N,2048]); large maps stay NHWC so that U-Net / ResNet blocks chain and
         # torch.cat (pix2pix/models.py:50) without a layout round trip per block.
         want_contiguous = x.is_contiguous()
         stats = None
-        for s in steps:
+        queue = list(steps)
+        while queue:
+            s = queue.pop(0)
+            if isinstance(s, _TailStep):
+                ns, cs = s.norm_step, s.conv_step
+                norm, conv = ns.norm, cs.conv
+                if (norm.training and x.shape[1] == conv.in_channels and x.shape[1] == norm.num_features
+                        and ops.tail_supported(tuple(x.shape), conv.out_channels, ns.act, ns.slope, cs.act)):
+                    rm = rv = nbt = None
+                    momentum = 0.0
+                    if norm.track_running_stats and norm.running_mean is not None:
+                        if norm.momentum is None:
+                            raise NotImplementedError("b200gan: BatchNorm2d(momentum=None)")
+                        rm, rv, nbt, momentum = norm.running_mean, norm.running_var, norm.num_batches_tracked, float(norm.momentum)
+                    spec = F.TailSpec(eps=float(norm.eps), momentum=momentum, act_mid=ns.act, slope=ns.slope,
+                                      act_out=cs.act, rtf_dx=ns.rtf_dx)
+                    x = F.TailFn.apply(x, stats if ns.takes_stats else None, norm.weight, norm.bias, rm, rv, nbt,
+                                       conv.weight, conv.bias, spec)
+                    stats = None
+                else:
+                    queue[0:0] = [ns, cs]
+                continue
             if isinstance(s, _ConvStep):
                 cs = None
                 if s.dropout2d is not None and s.dropout2d.training and s.dropout2d.p > 0.0:
                     n = x.shape[0]
                     cs = _dropout2d_scale((n, s.conv.out_channels), s.dropout2d.p, x.device)
-                out = _run_conv(s.conv, x, s.up, s.extra_pads, s.pad_mode, s.act, s.slope, cs, s.stats, s.rtf_out,
+                # fused statistics only when the following norm really normalises with batch statistics (an eval-mode
+                # BatchNorm2d never consumes -- and so never re-zeroes -- the shared accumulator)
+                want = s.stats if (s.next_norm is not None and _uses_batch_stats(s.next_norm)) else None
+                out = _run_conv(s.conv, x, s.up, s.extra_pads, s.pad_mode, s.act, s.slope, cs, want, s.rtf_out,
                                 s.rtf_dz)
-                if s.stats is not None:
+                if want is not None:
                     x, stats = out
                 else:
                     x, stats = out, None

@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ALGO_SIMT, ALGO_TC, PAD_REFLECT, PAD_ZERO, ConvGeom, Epilogue, GpMlpDesc, NormDesc)
+from ._lib import (ACT_NONE, ALGO_SIMT, ALGO_TC, PAD_REFLECT, PAD_ZERO, ConvGeom, Epilogue, GpMlpDesc, NormDesc, TailDesc)
 
 CL = torch.channels_last
 
@@ -22,6 +22,8 @@ class Config:
     # a fused Sequential fed an NCHW-contiguous tensor returns an NCHW-contiguous tensor (what a script may .view,
     # dcgan.py:96) only for feature maps of at most this many pixels; larger maps stay channels_last
     contiguous_hw_limit = 64
+    # BatchNorm2d -> act -> Conv2d(C, K<=3, 3, 1, 1) -> act as the fused tail kernels (csrc/tail.cu)
+    fuse_tail = os.environ.get("B200GAN_FUSE_TAIL", "1") not in ("", "0")
 
 
 def _stream():
@@ -222,6 +224,64 @@ def norm_forward(x, gamma, beta, running_mean, running_var, nbt, per_sample, eps
     _lib.check(lib.b200gan_norm_apply(ctypes.byref(d), x.data_ptr(), scale_shift.data_ptr(), y.data_ptr(), st),
                "norm_apply")
     return y, mean_rstd
+
+
+def norm_finalize(x_shape, stats, gamma, beta, running_mean, running_var, nbt, per_sample, eps, momentum, device):
+    """Batch statistics -> (mean_rstd, scale_shift); updates the running statistics.  `stats` is consumed (zeroed)."""
+    n, c, h, w = x_shape
+    d = NormDesc()
+    d.N, d.HW, d.C, d.per_sample = n, h * w, c, int(per_sample)
+    d.eps, d.momentum, d.act, d.slope, d.round_tf32 = eps, momentum, ACT_NONE, 0.0, 0
+    groups = stats.numel() // 2
+    mean_rstd = torch.empty(2 * groups, device=device, dtype=torch.float32)
+    scale_shift = torch.empty(2 * groups, device=device, dtype=torch.float32)
+    _lib.check(_lib.load().b200gan_norm_finalize(ctypes.byref(d), stats.data_ptr(), _ptr(gamma), _ptr(beta),
+                                                 mean_rstd.data_ptr(), scale_shift.data_ptr(), _ptr(running_mean),
+                                                 _ptr(running_var), _ptr(nbt), _stream()), "norm_finalize")
+    return mean_rstd, scale_shift
+
+
+def norm_stats(x, per_sample):
+    d = _norm_desc(x, per_sample, 0.0, 0.0, ACT_NONE, 0.0, False)
+    stats = new_stats(x, per_sample)
+    _lib.check(_lib.load().b200gan_norm_stats(ctypes.byref(d), x.data_ptr(), stats.data_ptr(), _stream()), "norm_stats")
+    return stats
+
+
+# ---- Generator tail: BatchNorm2d -> act -> Conv2d(C, K<=3, 3, 1, 1) -> act (csrc/tail.cu) -------------------
+def tail_desc(a_shape, k, act_mid, slope, act_out):
+    n, c, h, w = a_shape
+    d = TailDesc()
+    d.N, d.H, d.W, d.C, d.K = n, h, w, c, k
+    d.act_mid, d.slope, d.act_out = act_mid, slope, act_out
+    return d
+
+
+def tail_supported(a_shape, k, act_mid, slope, act_out):
+    if Config.algo == "simt" or not Config.fuse_tail:
+        return False
+    return bool(_lib.load().b200gan_tail_supported(ctypes.byref(tail_desc(a_shape, k, act_mid, slope, act_out))))
+
+
+def tail_fprop(d, a, scale_shift, w, bias):
+    out = empty_cl(d.N, d.K, d.H, d.W, a.device)
+    _lib.check(_lib.load().b200gan_tail_fprop(ctypes.byref(d), a.data_ptr(), scale_shift.data_ptr(), w.data_ptr(),
+                                              _ptr(bias), out.data_ptr(), _stream()), "tail_fprop")
+    return out
+
+
+def tail_bwd(d, a, mean_rstd, scale_shift, w, g, need_affine, need_bias, round_tf32):
+    lib = _lib.load()
+    nws = lib.b200gan_tail_bwd_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty((nws + 7) // 8, device=a.device, dtype=torch.float64)
+    da = torch.empty_like(a, memory_format=CL)
+    dgb = torch.empty(2 * d.C, device=a.device, dtype=torch.float32) if need_affine else None
+    dw = torch.empty((d.K, d.C, 3, 3), device=a.device, dtype=torch.float32)
+    db = torch.empty(d.K, device=a.device, dtype=torch.float32) if need_bias else None
+    _lib.check(lib.b200gan_tail_bwd(ctypes.byref(d), a.data_ptr(), mean_rstd.data_ptr(), scale_shift.data_ptr(),
+                                    w.data_ptr(), g.data_ptr(), ws.data_ptr(), da.data_ptr(), _ptr(dgb), dw.data_ptr(),
+                                    _ptr(db), int(round_tf32), _stream()), "tail_bwd")
+    return da, dgb, dw, db
 
 
 def norm_apply_affine(x, scale_shift, per_sample, act=ACT_NONE, slope=0.0):

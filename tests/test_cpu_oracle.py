@@ -96,6 +96,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.Epilogue) == 40
     assert ctypes.sizeof(_lib.NormDesc) == 9 * 4
     assert ctypes.sizeof(_lib.GpMlpDesc) == 6 * 4
+    assert ctypes.sizeof(_lib.TailDesc) == 8 * 4
 
 
 def test_geometry_helper_matches_torch_shapes():
@@ -148,10 +149,14 @@ def test_fusion_plan_for_dcgan():
     from b200gan import nn as bnn, zoo
     g, d = zoo.DCGANGenerator(64), zoo.DCGANDiscriminator(64)
     kinds = [type(s).__name__ for s in bnn._build_plan(list(g.conv_blocks))]
-    assert kinds == ["_NormStep", "_ConvStep", "_NormStep", "_ConvStep", "_NormStep", "_ConvStep"]
+    # BatchNorm2d(64, .8) + LeakyReLU + Conv2d(64, 1, 3, 1, 1) + Tanh (dcgan.py:60-63) is the fused tail node
+    assert kinds == ["_NormStep", "_ConvStep", "_NormStep", "_ConvStep", "_TailStep"]
     steps = bnn._build_plan(list(g.conv_blocks))
-    assert steps[1].up == 2 and steps[3].up == 2 and steps[5].up == 1
-    assert steps[1].stats is False and steps[5].stats is None and steps[5].act == 3
+    tail = steps[4]
+    assert steps[1].up == 2 and steps[3].up == 2 and tail.conv_step.up == 1
+    assert steps[1].stats is False and steps[3].stats is False and steps[3].next_norm is g.conv_blocks[7]
+    assert tail.norm_step.takes_stats and tail.norm_step.act == 1 and tail.norm_step.rtf_dx
+    assert tail.conv_step.stats is None and tail.conv_step.act == 3
     dsteps = bnn._build_plan(list(d.model))
     assert [type(s).__name__ for s in dsteps] == ["_ConvStep", "_ConvStep", "_NormStep", "_ConvStep", "_NormStep",
                                                   "_ConvStep", "_NormStep"]
