@@ -263,6 +263,30 @@ int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, d
                       double beta1, double beta2, double eps, float grad_scale, float *step,
                       void *stream);
 
+/* ---- Discriminator head and adversarial loss (csrc/head.cu) --------------------------------------------------- */
+/* y[n] = act(dot(x[n], w) + b): nn.Linear(K, 1) [+ nn.Sigmoid]  (dcgan.py:92).  x [N][K] row-major. */
+int b200gan_linear1_fwd(const float *x, const float *w, const float *b, float *y, int32_t N, int32_t K, int32_t act,
+                        void *stream);
+/* Backward from the saved output y: dx [N][K] (may be NULL), dw [K], db [1] (may be NULL) are OVERWRITTEN. */
+int b200gan_linear1_bwd(const float *x, const float *w, const float *y, const float *dy, float *dx, float *dw,
+                        float *db, int32_t N, int32_t K, int32_t act, void *stream);
+/* torch.nn.BCELoss(), reduction 'mean', log terms clamped at -100 (dcgan.py:103,166,178-179). */
+int b200gan_bce_fwd(const float *v, const float *t, float *loss, int64_t n, void *stream);
+int b200gan_bce_bwd(const float *v, const float *t, const float *gout, float *dv, int64_t n, void *stream);
+
+/* Multi-tensor form: every parameter tensor of one optimizer in ONE launch (the table travels as a kernel argument;
+ * `g` is whatever tensor autograd left in param.grad).  step: TWO floats on the device, zero-initialised by the caller:
+ * step[0] = number of steps taken (advanced by the last block of the launch), step[1] = internal ticket counter. */
+typedef struct b200gan_adam_tensor {
+  float *p;
+  const float *g;
+  float *m;
+  float *v;
+  int64_t n;
+} b200gan_adam_tensor;
+int b200gan_adam_multi(const b200gan_adam_tensor *tensors, int32_t count, double lr, double beta1, double beta2,
+                       double eps, float grad_scale, float *step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,10 @@ class TailDesc(ctypes.Structure):
                 ("slope", c_f32), ("act_out", c_i32)]
 
 
+class AdamTensor(ctypes.Structure):
+    _fields_ = [("p", c_vp), ("g", c_vp), ("m", c_vp), ("v", c_vp), ("n", c_i64)]
+
+
 # name -> (restype, argtypes); must list every function declared in include/b200gan.h
 _P = ctypes.POINTER
 SIGNATURES = {
@@ -81,6 +85,11 @@ SIGNATURES = {
     "b200gan_gp_mlp_workspace_floats": (c_sz, [_P(GpMlpDesc)]),
     "b200gan_gp_mlp_fwd_bwd": (c_i32, [_P(GpMlpDesc)] + [c_vp] * 12),
     "b200gan_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f32, c_vp, c_vp]),
+    "b200gan_linear1_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "b200gan_linear1_bwd": (c_i32, [c_vp] * 7 + [c_i32, c_i32, c_i32, c_vp]),
+    "b200gan_bce_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "b200gan_bce_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "b200gan_adam_multi": (c_i32, [_P(AdamTensor), c_i32, c_f64, c_f64, c_f64, c_f64, c_f32, c_vp, c_vp]),
 }
 
 _lib = None

@@ -329,6 +329,50 @@ class ActFn(torch.autograd.Function):
         return ops.epilogue_bwd(dy, y, mask, ctx.act, ctx.slope), None, None, None, None
 
 
+class Linear1Fn(torch.autograd.Function):
+    """nn.Linear(K, 1) [+ Sigmoid/Tanh/...] on a 2-D CUDA tensor: the discriminator head (dcgan.py:92)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        ops._require_cuda(x, "linear input")
+        x = x.contiguous()
+        y = ops.linear1_fwd(x, weight.detach().contiguous(), None if bias is None else bias.detach(), act)
+        ctx.act, ctx.has_bias = act, bias is not None
+        ctx.save_for_backward(x, weight, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        if torch.is_grad_enabled():  # create_graph=True: stay differentiable (plain torch ops on the saved tensors)
+            if ctx.act == ACT_SIGMOID:
+                dl = dy * y * (1 - y)
+            elif ctx.act == ACT_TANH:
+                dl = dy * (1 - y * y)
+            else:
+                dl = dy
+            return dl @ weight, dl.t() @ x, (dl.sum(0) if ctx.has_bias else None), None
+        dx, dw, db = ops.linear1_bwd(x, weight.detach().contiguous(), y, dy.contiguous(), ctx.act,
+                                     ctx.needs_input_grad[0], ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dw if ctx.needs_input_grad[1] else None, db, None
+
+
+class BCEMeanFn(torch.autograd.Function):
+    """torch.nn.BCELoss() (reduction 'mean') forward and backward as one kernel each (dcgan.py:103,166)."""
+
+    @staticmethod
+    def forward(ctx, v, t):
+        v, t = v.contiguous(), t.contiguous()
+        ctx.save_for_backward(v, t)
+        return ops.bce_fwd(v, t)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        v, t = ctx.saved_tensors
+        return ops.bce_bwd(v, t, gout.contiguous()), None
+
+
 def conv_block(x, weight, bias, chan_scale, spec, cache):
     return ConvFn.apply(x, weight, bias, chan_scale, spec, cache)
 

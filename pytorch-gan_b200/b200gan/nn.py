@@ -20,7 +20,7 @@ from .functional import ConvSpec, NormSpec, PackCache
 _T = {  # the stock classes, captured before any patching
     n: getattr(tnn, n) for n in (
         "Conv2d", "ConvTranspose2d", "BatchNorm2d", "InstanceNorm2d", "LeakyReLU", "ReLU", "Tanh", "Sigmoid",
-        "Upsample", "ZeroPad2d", "ReflectionPad2d", "Dropout", "Dropout2d", "Sequential")
+        "Upsample", "ZeroPad2d", "ReflectionPad2d", "Dropout", "Dropout2d", "Sequential", "Linear", "BCELoss")
 }
 
 
@@ -241,6 +241,25 @@ class Dropout(_T["Dropout"]):
         return F.ActFn.apply(xc, ACT_NONE, 0.0, mask, False)
 
 
+def _gpu2d_f32(x):
+    return torch.is_tensor(x) and x.dim() == 2 and x.is_cuda and x.dtype == torch.float32
+
+
+class Linear(_T["Linear"]):
+    """nn.Linear.  Inside a Sequential, Linear(K, 1) + Sigmoid -- the head of a discriminator (dcgan.py:92) -- runs as
+    one b200gan kernel per direction (Sequential._forward_2d); on its own it is a plain library GEMM and stays on
+    torch/cuBLAS (wgan_gp.py:46-60,72-78; dcgan.py:50), which also keeps the critic of wgan_gp.py double-differentiable
+    for the script's own autograd.grad(create_graph=True)."""
+
+
+class BCELoss(_T["BCELoss"]):
+    def forward(self, input, target):
+        if (input.is_cuda and input.dtype == torch.float32 and self.reduction == "mean" and self.weight is None
+                and target.shape == input.shape and target.dtype == torch.float32 and not target.requires_grad):
+            return F.BCEMeanFn.apply(input, target)
+        return super().forward(input, target)
+
+
 # ---- fusion planner ------------------------------------------------------------------------------------
 class _ConvStep:
     def __init__(self, conv, up, extra_pads, pad_mode, act, slope, dropout2d, stats):
@@ -379,7 +398,25 @@ class Sequential(_T["Sequential"]):
             self.__dict__["_b200_plan"] = cached
         return cached[1]
 
+    def _forward_2d(self, x):
+        """Matrix input (the adv_layer of a discriminator, dcgan.py:92): Linear(K, 1) + activation as one node."""
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if (isinstance(m, _T["Linear"]) and m.out_features == 1 and _gpu2d_f32(x) and x.shape[0] <= 4096
+                    and i + 1 < len(mods) and _act_of(mods[i + 1]) is not None
+                    and _act_of(mods[i + 1])[0] in (ACT_SIGMOID, ACT_TANH)):
+                x = F.Linear1Fn.apply(x, m.weight, m.bias, _act_of(mods[i + 1])[0])
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x
+
     def forward(self, x):
+        if _gpu2d_f32(x):
+            return self._forward_2d(x)
         if not (torch.is_tensor(x) and x.dim() == 4 and x.is_cuda and x.dtype == torch.float32):
             return super().forward(x)
         steps = self._plan()
@@ -442,7 +479,7 @@ REPLACEMENTS = {
     "Conv2d": Conv2d, "ConvTranspose2d": ConvTranspose2d, "BatchNorm2d": BatchNorm2d,
     "InstanceNorm2d": InstanceNorm2d, "LeakyReLU": LeakyReLU, "ReLU": ReLU, "Tanh": Tanh, "Sigmoid": Sigmoid,
     "Upsample": Upsample, "ZeroPad2d": ZeroPad2d, "ReflectionPad2d": ReflectionPad2d, "Dropout": Dropout,
-    "Dropout2d": Dropout2d, "Sequential": Sequential,
+    "Dropout2d": Dropout2d, "Sequential": Sequential, "Linear": Linear, "BCELoss": BCELoss,
 }
 for _n, _c in REPLACEMENTS.items():
     _c.__name__ = _n

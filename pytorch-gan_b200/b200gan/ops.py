@@ -349,6 +349,38 @@ def act_forward(x, act, slope, mask=None, mask_per_channel=False):
     return y
 
 
+# ---- Discriminator head / adversarial loss (csrc/head.cu) ----------------------------------------------------
+def linear1_fwd(x, w, b, act):
+    n, k = x.shape
+    y = torch.empty((n, 1), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().b200gan_linear1_fwd(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), n, k, act, _stream()),
+               "linear1_fwd")
+    return y
+
+
+def linear1_bwd(x, w, y, dy, act, need_dx, need_db):
+    n, k = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty((1, k), device=x.device, dtype=torch.float32)
+    db = torch.empty(1, device=x.device, dtype=torch.float32) if need_db else None
+    _lib.check(_lib.load().b200gan_linear1_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dx),
+                                               dw.data_ptr(), _ptr(db), n, k, act, _stream()), "linear1_bwd")
+    return dx, dw, db
+
+
+def bce_fwd(v, t):
+    loss = torch.empty((), device=v.device, dtype=torch.float32)
+    _lib.check(_lib.load().b200gan_bce_fwd(v.data_ptr(), t.data_ptr(), loss.data_ptr(), v.numel(), _stream()), "bce_fwd")
+    return loss
+
+
+def bce_bwd(v, t, gout):
+    dv = torch.empty_like(v)
+    _lib.check(_lib.load().b200gan_bce_bwd(v.data_ptr(), t.data_ptr(), gout.data_ptr(), dv.data_ptr(), v.numel(),
+                                           _stream()), "bce_bwd")
+    return dv
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, grad_scale, step):
     _lib.check(_lib.load().b200gan_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
                                              beta1, beta2, eps, grad_scale, step.data_ptr(), _stream()), "adam_step")

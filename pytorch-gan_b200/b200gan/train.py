@@ -22,6 +22,23 @@ def frozen(module):
             p.requires_grad_(True)
 
 
+def _opt_step(opt, reducer):
+    """optimizer.step(), preceded by the data-parallel gradient all-reduce when a reducer is given (ddp.py)."""
+    if reducer is None:
+        opt.step()
+    elif hasattr(reducer, "reduce_and_step"):
+        reducer.reduce_and_step(opt)
+    else:
+        reducer()
+        opt.step()
+
+
+def _join(*reducers):
+    for r in reducers:
+        if r is not None and hasattr(r, "join"):
+            r.join()
+
+
 def dcgan_step(generator, discriminator, opt_g, opt_d, real_imgs, z, loss=None, valid=None, fake=None,
                reduce_g=None, reduce_d=None, skip_dead_wgrad=True):
     """implementations/dcgan/dcgan.py:146-183.  `reduce_*`: optional gradient all-reduce hooks invoked
@@ -36,21 +53,19 @@ def dcgan_step(generator, discriminator, opt_g, opt_d, real_imgs, z, loss=None, 
     with frozen(discriminator) if skip_dead_wgrad else contextlib.nullcontext():
         g_loss = loss(discriminator(gen_imgs), valid)        # :166
         g_loss.backward()                                    # :168
-    if reduce_g is not None:
-        reduce_g()
-    opt_g.step()                                             # :169
+    _opt_step(opt_g, reduce_g)                               # :169 (all-reduce + Adam may overlap the D phase below)
     opt_d.zero_grad()                                        # :175
     real_loss = loss(discriminator(real_imgs), valid)        # :178
     fake_loss = loss(discriminator(gen_imgs.detach()), fake) # :179
     d_loss = (real_loss + fake_loss) / 2                     # :180
     d_loss.backward()                                        # :182
-    if reduce_d is not None:
-        reduce_d()
-    opt_d.step()                                             # :183
+    _opt_step(opt_d, reduce_d)                               # :183
+    _join(reduce_g, reduce_d)
     return g_loss.detach(), d_loss.detach(), gen_imgs.detach()
 
 
-def wgan_gp_critic_step(generator, discriminator, opt_d, real_imgs, z, alpha, lambda_gp=10.0, fused_gp=True):
+def wgan_gp_critic_step(generator, discriminator, opt_d, real_imgs, z, alpha, lambda_gp=10.0, fused_gp=True,
+                        reduce_d=None):
     """One critic iteration of implementations/wgan_gp/wgan_gp.py:155-174.  `alpha` [N,1,1,1] is the
     interpolation weight the reference draws with numpy (wgan_gp.py:122).  With fused_gp the penalty and its
     double backward run in the single gp_mlp kernel; otherwise through autograd exactly like the reference.
@@ -74,7 +89,8 @@ def wgan_gp_critic_step(generator, discriminator, opt_d, real_imgs, z, alpha, la
         gp_term = lambda_gp * ((grads.norm(2, dim=1) - 1) ** 2).mean()    # :137
     d_loss = -torch.mean(real_validity) + torch.mean(fake_validity) + gp_term   # :171
     d_loss.backward()                                                     # :173
-    opt_d.step()                                                          # :174
+    _opt_step(opt_d, reduce_d)                                            # :174
+    _join(reduce_d)
     return d_loss.detach(), gp_term.detach()
 
 
@@ -88,7 +104,8 @@ def wgan_gp_generator_step(generator, discriminator, opt_g, z):
     return g_loss.detach()
 
 
-def pix2pix_step(generator, discriminator, opt_g, opt_d, real_a, real_b, lambda_pixel=100.0):
+def pix2pix_step(generator, discriminator, opt_g, opt_d, real_a, real_b, lambda_pixel=100.0, reduce_g=None,
+                 reduce_d=None):
     """implementations/pix2pix/pix2pix.py:131-172 (MSE GAN loss :50, L1 pixel loss :51,:54)."""
     mse, l1 = torch.nn.functional.mse_loss, torch.nn.functional.l1_loss
     opt_g.zero_grad()                                          # :138
@@ -98,13 +115,14 @@ def pix2pix_step(generator, discriminator, opt_g, opt_d, real_a, real_b, lambda_
         valid = torch.ones_like(pred_fake)                     # :131
         loss_g = mse(pred_fake, valid) + lambda_pixel * l1(fake_b, real_b)   # :143-148
         loss_g.backward()                                      # :150
-    opt_g.step()                                               # :152
+    _opt_step(opt_g, reduce_g)                                 # :152
     opt_d.zero_grad()                                          # :158
     loss_real = mse(discriminator(real_b, real_a), valid)      # :161-162
     loss_fake = mse(discriminator(fake_b.detach(), real_a), torch.zeros_like(valid))   # :165-166
     loss_d = 0.5 * (loss_real + loss_fake)                     # :169
     loss_d.backward()                                          # :171
-    opt_d.step()                                               # :172
+    _opt_step(opt_d, reduce_d)                                 # :172
+    _join(reduce_g, reduce_d)
     return loss_g.detach(), loss_d.detach()
 
 
@@ -134,7 +152,7 @@ class ReplayBuffer:
 
 
 def cyclegan_step(g_ab, g_ba, d_a, d_b, opt_g, opt_d_a, opt_d_b, real_a, real_b, buf_a=None, buf_b=None,
-                  lambda_cyc=10.0, lambda_id=5.0):
+                  lambda_cyc=10.0, lambda_id=5.0, reduce_g=None, reduce_d_a=None, reduce_d_b=None):
     """implementations/cyclegan/cyclegan.py:163-241: 6 generator passes + 2 D passes for the G loss, then one
     step per discriminator on (real, replayed fake).  buf_* = ReplayBuffer or None (fakes used directly)."""
     mse, l1 = torch.nn.functional.mse_loss, torch.nn.functional.l1_loss
@@ -149,16 +167,18 @@ def cyclegan_step(g_ab, g_ba, d_a, d_b, opt_g, opt_d_a, opt_d_b, real_a, real_b,
         loss_cycle = (l1(g_ba(fake_b), real_a) + l1(g_ab(fake_a), real_b)) / 2  # :194-199
         loss_g = loss_gan + lambda_cyc * loss_cycle + lambda_id * loss_identity  # :202
         loss_g.backward()                                                      # :204
-    opt_g.step()                                                               # :205
+    _opt_step(opt_g, reduce_g)                                                 # :205
     fake = torch.zeros_like(valid)                                             # :167
     losses_d = []
-    for d, opt, real, fk, buf in ((d_a, opt_d_a, real_a, fake_a, buf_a), (d_b, opt_d_b, real_b, fake_b, buf_b)):
+    for d, opt, real, fk, buf, red in ((d_a, opt_d_a, real_a, fake_a, buf_a, reduce_d_a),
+                                       (d_b, opt_d_b, real_b, fake_b, buf_b, reduce_d_b)):
         opt.zero_grad()                                                        # :211 / :228
         fk_ = buf.push_and_pop(fk) if buf is not None else fk.detach()         # :216 / :233
         loss_d = (mse(d(real), valid) + mse(d(fk_.detach()), fake)) / 2        # :214-219
         loss_d.backward()                                                      # :221
-        opt.step()                                                             # :222
+        _opt_step(opt, red)                                                    # :222
         losses_d.append(loss_d.detach())
+    _join(reduce_g, reduce_d_a, reduce_d_b)
     return loss_g.detach(), (losses_d[0] + losses_d[1]) / 2
 
 

@@ -236,6 +236,62 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
 }
 __global__ void adam_step_inc_kernel(float *step) { *step += 1.f; }
 
+// Multi-tensor form: ONE launch updates every parameter tensor of an optimizer.  The tensor table travels as a kernel
+// argument (no device-side table to maintain; addresses are whatever autograd produced this step, or the fixed
+// addresses of a captured CUDA graph).  Block b works on chunk (b - block_begin[t]) of tensor t; the last block to
+// finish (atomicInc ticket, self-resetting) advances the device-side step count, so there is no second launch.
+constexpr int ADAM_MAX_TENSORS = 48;
+constexpr int ADAM_CHUNK = 256 * 16;  // elements per block
+struct AdamTable {
+  float *p[ADAM_MAX_TENSORS];
+  const float *g[ADAM_MAX_TENSORS];
+  float *m[ADAM_MAX_TENSORS];
+  float *v[ADAM_MAX_TENSORS];
+  long long n[ADAM_MAX_TENSORS];
+  int block_begin[ADAM_MAX_TENSORS + 1];
+  int count;
+};
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamTable tb, double lr, double b1, double b2, double eps, float gscale,
+                  float *__restrict__ step, int advance) {
+  const double t = (double)step[0] + 1.0;
+  const float neg_step_size = (float)(-(lr / (1.0 - pow(b1, t))));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(b2, t));
+  const float b1f = (float)b1, omb1 = (float)(1.0 - b1), b2f = (float)b2, omb2 = (float)(1.0 - b2);
+  const float epsf = (float)eps;
+  int lo = 0, hi = tb.count;  // tensor of this block: largest ti with block_begin[ti] <= blockIdx.x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tb.block_begin[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const int ti = lo;
+  float *__restrict__ p = tb.p[ti];
+  const float *__restrict__ g = tb.g[ti];
+  float *__restrict__ m = tb.m[ti];
+  float *__restrict__ v = tb.v[ti];
+  const long long n = tb.n[ti];
+  const long long i0 = (long long)((int)blockIdx.x - tb.block_begin[ti]) * ADAM_CHUNK;
+  long long i1 = i0 + ADAM_CHUNK;
+  if (i1 > n) i1 = n;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const float gi = g[i] * gscale;
+    const float mi = b1f * m[i] + omb1 * gi;
+    const float vi = b2f * v[i] + omb2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + epsf;
+    p[i] += neg_step_size * (mi / denom);
+  }
+  if (advance) {
+    __syncthreads();  // every thread of this block has read step[0]
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned *ticket = reinterpret_cast<unsigned *>(step + 1);
+      if (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) step[0] = (float)t;  // last block; ticket wrapped to 0
+    }
+  }
+}
+
 static unsigned stream_blocks(int64_t n) {
   int64_t b = ceil_div64(n, 256);
   if (b > 148 * 16) b = 148 * 16;
@@ -335,6 +391,35 @@ extern "C" int b200gan_adam_step(float *p, const float *g, float *m, float *v, i
   }
   adam_step_inc_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
   B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_adam_multi(const b200gan_adam_tensor *tensors, int32_t count, double lr, double beta1,
+                                  double beta2, double eps, float grad_scale, float *step, void *stream) {
+  B2_CHECK_ARG(step != nullptr && (count == 0 || tensors != nullptr) && count >= 0, "adam_multi: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (count == 0) {
+    adam_step_inc_kernel<<<1, 1, 0, st>>>(step);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
+  for (int base = 0; base < count; base += ADAM_MAX_TENSORS) {
+    AdamTable tb;
+    const int c = count - base < ADAM_MAX_TENSORS ? count - base : ADAM_MAX_TENSORS;
+    int blocks = 0;
+    for (int i = 0; i < c; ++i) {
+      const b200gan_adam_tensor &t = tensors[base + i];
+      B2_CHECK_ARG(t.p && t.g && t.m && t.v && t.n > 0, "adam_multi: tensor %d has a null pointer or no elements", base + i);
+      tb.p[i] = t.p; tb.g[i] = t.g; tb.m[i] = t.m; tb.v[i] = t.v; tb.n[i] = t.n;
+      tb.block_begin[i] = blocks;
+      blocks += (int)ceil_div64(t.n, ADAM_CHUNK);
+    }
+    tb.block_begin[c] = blocks;
+    tb.count = c;
+    const int last = base + c >= count;
+    adam_multi_kernel<<<(unsigned)blocks, 256, 0, st>>>(tb, lr, beta1, beta2, eps, grad_scale, step, last);
+    B2_LAUNCH_CHECK();
+  }
   return B200GAN_OK;
 }
 

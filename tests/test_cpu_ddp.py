@@ -37,9 +37,15 @@ def _worker(rank, world, port, out):
     reducer = ddp.GradReducer(list(net.parameters()), world)
     loss = torch.nn.MSELoss()(net(x_all[shard]), y_all[shard])
     loss.backward()
-    reducer()            # all-reduce(sum) / world, right before the optimizer step (dcgan.py:169,183)
-    grads = [p.grad.clone() for p in net.parameters()]
-    opt.step()
+    if rank == 0:
+        reducer()        # all-reduce(sum) / world, right before the optimizer step (dcgan.py:169,183)
+        grads = [p.grad.clone() for p in net.parameters()]
+        opt.step()
+    else:                # the form the training steps use (train._opt_step): reduce + step in one call
+        from b200gan import train
+        train._opt_step(opt, reducer)
+        train._join(reducer)
+        grads = [p.grad.clone() for p in net.parameters()]
     out[rank] = (grads, [p.detach().clone() for p in net.parameters()])
     dist.destroy_process_group()
 

@@ -357,3 +357,34 @@ def test_empty_batch_and_errors():
         conv(torch.zeros(1, 5, 8, 8, device="cuda"))
     with pytest.raises(NotImplementedError):
         bnn.Conv2d(4, 4, 3, 1, 1, groups=2).cuda()(torch.zeros(1, 4, 8, 8, device="cuda"))
+
+
+def test_discriminator_head_and_bce_match_stock_torch():
+    """Sequential(Linear(2048, 1), Sigmoid) + BCELoss (dcgan.py:92,103): one kernel per direction each."""
+    from b200gan import nn as bnn
+    torch.manual_seed(11)
+    ref = torch.nn.Sequential(torch.nn.Linear(2048, 1), torch.nn.Sigmoid()).cuda()
+    ours = bnn.Sequential(bnn.Linear(2048, 1), bnn.Sigmoid()).cuda()
+    ours.load_state_dict(ref.state_dict())
+    for n in (128, 7):
+        x = torch.randn(n, 2048, device="cuda") * 0.5
+        for tgt in (1.0, 0.0, 0.3):
+            t = torch.full((n, 1), tgt, device="cuda")
+            xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            ref.zero_grad(); ours.zero_grad()
+            vr, vo = ref(xr), ours(xo)
+            assert rel_err(vo, vr) < 1e-5
+            lr_, lo = torch.nn.BCELoss()(vr, t), bnn.BCELoss()(vo, t)
+            assert abs(lo.item() - lr_.item()) < 1e-5 * abs(lr_.item())
+            lr_.backward(); lo.backward()
+            assert rel_err(xo.grad, xr.grad) < 1e-5
+            assert rel_err(ours[0].weight.grad, ref[0].weight.grad) < 1e-5
+            assert rel_err(ours[0].bias.grad, ref[0].bias.grad) < 1e-5
+    # saturated inputs: the clamps of torch's BCE (log >= -100, denominator >= 1e-12)
+    v = torch.tensor([[0.0], [1.0], [1e-30], [0.5]], device="cuda")
+    t = torch.tensor([[1.0], [0.0], [0.0], [1.0]], device="cuda")
+    vr, vo = v.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    lr_, lo = torch.nn.BCELoss()(vr, t), bnn.BCELoss()(vo, t)
+    assert abs(lo.item() - lr_.item()) < 1e-5 * abs(lr_.item())
+    lr_.backward(); lo.backward()
+    assert rel_err(vo.grad, vr.grad) < 1e-5
