@@ -76,6 +76,10 @@ class Adam(torch.optim.Optimizer):
             _lib.check(lib.b200gan_adam_multi(table, len(rows), float(group["lr"]), float(b1), float(b2),
                                               float(group["eps"]), float(self.grad_scale), st["step"].data_ptr(),
                                               torch.cuda.current_stream().cuda_stream), "adam_multi")
+            # the kernel wrote the parameters behind autograd's back: bump their version counters, which is what
+            # invalidates the packed-weight caches of the conv modules (functional.PackCache) -- no kernel involved
+            torch.autograd.graph.increment_version([p for p in st["params"] if p.grad is not None or
+                                                    (self.grad_override and p in self.grad_override)])
         return loss
 
     def state_dict(self):

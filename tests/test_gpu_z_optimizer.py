@@ -103,3 +103,27 @@ def test_multi_tensor_adam_in_a_cuda_graph():
     # the capture itself does not execute; warm-up + 3 replays = 4 steps
     assert ours.state[q]["step"].item() == 4.0
     assert torch.allclose(q, p, rtol=6e-7, atol=1e-8)
+
+
+def test_adam_step_invalidates_the_packed_weight_caches():
+    """The optimizer kernel writes parameters through raw pointers; the conv modules' packed (tcgen05 / SIMT) weight
+    copies are keyed on the tensor version counter, which optim.Adam bumps.  Forward after a step must use the NEW
+    weights (fprop and dgrad read packed copies)."""
+    from b200gan import nn as bnn, optim
+    torch.manual_seed(9)
+    for cin, cout in ((64, 64), (3, 8)):      # tcgen05 path and SIMT path
+        ours = bnn.Conv2d(cin, cout, 3, 1, 1).cuda()
+        ref = torch.nn.Conv2d(cin, cout, 3, 1, 1).cuda()
+        ref.load_state_dict(ours.state_dict())
+        oo = optim.Adam(ours.parameters(), lr=1e-2, betas=(0.5, 0.999))
+        orf = torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.5, 0.999))
+        x = torch.randn(2, cin, 16, 16, device="cuda")
+        for _ in range(3):
+            xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            yo, yr = ours(xo), ref(xr)
+            assert rel_err(yo, yr) < 2e-3
+            oo.zero_grad(); orf.zero_grad()
+            yo.square().mean().backward(); yr.square().mean().backward()
+            assert rel_err(xo.grad, xr.grad) < 5e-3
+            oo.step(); orf.step()
+        assert rel_err(ours.weight, ref.weight) < 1e-3
