@@ -111,6 +111,16 @@ size_t b200gan_packed_weight_floats(const b200gan_conv_geom *g, int pack);
 int b200gan_pack_weights(const b200gan_conv_geom *g, int pack, const float *w, float *packed,
                          void *stream);
 
+/* Every packed copy of an optimizer's weights in ONE launch (the job table travels as a kernel argument): called by
+ * b200gan.optim.Adam right after the parameter update, so a training step carries 2 pack launches instead of ~20. */
+typedef struct b200gan_pack_job {
+  const float *w;
+  float *packed;
+  b200gan_conv_geom geom;
+  int32_t pack; /* B200GAN_PACK_* */
+} b200gan_pack_job;
+int b200gan_pack_weights_multi(const b200gan_pack_job *jobs, int32_t count, void *stream);
+
 /* ---- convolution: forward, data gradient, weight gradient ---------------------------- */
 /* 1 if algo (B200GAN_ALGO_TC) supports this geometry for the given pass (0 fprop,1 dgrad,2 wgrad) */
 int b200gan_conv2d_supported(const b200gan_conv_geom *g, int pass, int algo);

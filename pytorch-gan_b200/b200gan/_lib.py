@@ -42,6 +42,10 @@ class GpMlpDesc(ctypes.Structure):
                 ("lambda_gp", c_f32)]
 
 
+class PackJob(ctypes.Structure):
+    _fields_ = [("w", c_vp), ("packed", c_vp), ("geom", ConvGeom), ("pack", c_i32)]
+
+
 class TailDesc(ctypes.Structure):
     _fields_ = [("N", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32), ("K", c_i32), ("act_mid", c_i32),
                 ("slope", c_f32), ("act_out", c_i32)]
@@ -59,6 +63,7 @@ SIGNATURES = {
     "b200gan_check_device": (c_i32, []),
     "b200gan_packed_weight_floats": (c_sz, [_P(ConvGeom), c_i32]),
     "b200gan_pack_weights": (c_i32, [_P(ConvGeom), c_i32, c_vp, c_vp, c_vp]),
+    "b200gan_pack_weights_multi": (c_i32, [_P(PackJob), c_i32, c_vp]),
     "b200gan_conv2d_supported": (c_i32, [_P(ConvGeom), c_i32, c_i32]),
     "b200gan_conv2d_fprop": (c_i32, [_P(ConvGeom), _P(Epilogue), c_vp, c_vp, c_vp, c_i32, c_vp]),
     "b200gan_conv2d_dgrad_workspace_floats": (c_sz, [_P(ConvGeom), c_i32]),

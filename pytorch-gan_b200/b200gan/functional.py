@@ -5,12 +5,14 @@ Reference behaviour mirrored (file:line under implementations/):
   conv blocks        dcgan/dcgan.py:52-64, 77-88   pix2pix/models.py:20-52   cyclegan/models.py:22-87
   training-mode BN   dcgan/dcgan.py:53,56,60,80 (eps = 0.8)    InstanceNorm  pix2pix/models.py:25,40
 """
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch
 
 from . import ops
+from ._lib import ConvGeom
 from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ALGO_AUTO, ALGO_SIMT, ALGO_TC, PACK_SIMT_DGRAD,
                    PACK_SIMT_FPROP, PACK_TC_DGRAD, PACK_TC_DGRAD_UP2, PACK_TC_FPROP, PACK_TC_FPROP_UP2, PAD_ZERO)
 
@@ -41,7 +43,11 @@ class NormSpec:
 
 
 class PackCache:
-    """Derived packed copies of one weight Parameter, invalidated by the tensor version counter."""
+    """Derived packed copies of one weight Parameter, invalidated by the tensor version counter.  Caches register
+    themselves per parameter so that an optimizer can refresh every packed copy of its weights in ONE launch right
+    after the update (refresh_packs) instead of one pack launch per copy at the next forward."""
+
+    registry = weakref.WeakValueDictionary()  # id(parameter storage) -> PackCache
 
     def __init__(self):
         self._d = {}
@@ -52,9 +58,41 @@ class PackCache:
         hit = self._d.get(key)
         if ops.Config.weight_cache and hit is not None and hit[0] == ver:
             return hit[1]
-        packed = ops.pack_weights(g, w, kind)
-        self._d[key] = (ver, packed)
+        if hit is not None and hit[1].device == w.device:
+            packed = hit[1]          # same buffer: a CUDA graph that captured it stays valid
+            ops.pack_weights(g, w, kind, out=packed)
+        else:
+            packed = ops.pack_weights(g, w, kind)
+        g_copy = ConvGeom.from_buffer_copy(g)
+        self._d[key] = (ver, packed, g_copy)
+        PackCache.registry[w.data_ptr()] = self
         return packed
+
+    def jobs(self, w):
+        """(geometry, kind, packed buffer) of every live copy, for ops.pack_weights_multi."""
+        return [(e[2], key[0], e[1]) for key, e in self._d.items() if e[1].device == w.device]
+
+    def mark_fresh(self, w):
+        ver = (w._version, w.data_ptr())
+        for key, e in list(self._d.items()):
+            self._d[key] = (ver, e[1], e[2])
+
+
+def refresh_packs(params):
+    """Re-pack, in one launch, every cached packed copy of the given (just updated) weight tensors."""
+    jobs, touched = [], []
+    for w in params:
+        cache = PackCache.registry.get(w.data_ptr())
+        if cache is None:
+            continue
+        js = cache.jobs(w)
+        if js:
+            jobs.extend((g, kind, w, packed) for g, kind, packed in js)
+            touched.append((cache, w))
+    if jobs:
+        ops.pack_weights_multi(jobs)
+        for cache, w in touched:
+            cache.mark_fresh(w)
 
 
 def _pow2ceil(v):

@@ -110,12 +110,21 @@ def tc_supported(g, pas):
     return bool(_lib.load().b200gan_conv2d_supported(ctypes.byref(g), pas, ALGO_TC))
 
 
-def pack_weights(g, w, kind):
+def pack_weights(g, w, kind, out=None):
     lib = _lib.load()
-    n = lib.b200gan_packed_weight_floats(ctypes.byref(g), kind)
-    out = torch.empty(n, device=w.device, dtype=torch.float32)
+    if out is None:
+        n = lib.b200gan_packed_weight_floats(ctypes.byref(g), kind)
+        out = torch.empty(n, device=w.device, dtype=torch.float32)
     _lib.check(lib.b200gan_pack_weights(ctypes.byref(g), kind, w.data_ptr(), out.data_ptr(), _stream()), "pack_weights")
     return out
+
+
+def pack_weights_multi(jobs):
+    """jobs: [(ConvGeom, kind, weight tensor, packed buffer)] -- one launch for all of them."""
+    table = (_lib.PackJob * len(jobs))()
+    for i, (g, kind, w, packed) in enumerate(jobs):
+        table[i].w, table[i].packed, table[i].geom, table[i].pack = w.data_ptr(), packed.data_ptr(), g, kind
+    _lib.check(_lib.load().b200gan_pack_weights_multi(table, len(jobs), _stream()), "pack_weights_multi")
 
 
 def conv_fprop(g, x, packed, algo, bias=None, act=ACT_NONE, slope=0.0, chan_scale=None, stats=None,

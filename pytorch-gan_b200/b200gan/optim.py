@@ -78,8 +78,11 @@ class Adam(torch.optim.Optimizer):
                                               torch.cuda.current_stream().cuda_stream), "adam_multi")
             # the kernel wrote the parameters behind autograd's back: bump their version counters, which is what
             # invalidates the packed-weight caches of the conv modules (functional.PackCache) -- no kernel involved
-            torch.autograd.graph.increment_version([p for p in st["params"] if p.grad is not None or
-                                                    (self.grad_override and p in self.grad_override)])
+            updated = [p for p in st["params"] if p.grad is not None or (self.grad_override and p in self.grad_override)]
+            torch.autograd.graph.increment_version(updated)
+            # ... and refresh every packed copy of the updated conv weights in one launch
+            from . import functional
+            functional.refresh_packs([p for p in updated if p.dim() == 4])
         return loss
 
     def state_dict(self):

@@ -123,9 +123,97 @@ __global__ void pack_up2_kernel(const float *__restrict__ src, float *__restrict
   }
 }
 
+// ---- every packed copy of an optimizer's weights in ONE launch ---------------------------------------------------
+// The weights change once per optimizer step, and every conv keeps 1-2 packed copies (fprop / dgrad layouts): per-copy
+// pack launches were 21 of the DCGAN step's launches.  The job table travels as a kernel argument.
+constexpr int PACK_MAX_JOBS = 24;
+constexpr int PACK_CHUNK = 256 * 8;  // packed elements per block
+struct PackJob {
+  const float *src;
+  float *dst;
+  int R, S, Cin, Cout, transposed, kind;
+  long long total;
+};
+struct PackTable {
+  PackJob job[PACK_MAX_JOBS];
+  int block_begin[PACK_MAX_JOBS + 1];
+  int count;
+};
+__device__ __forceinline__ float pack_element(const PackJob &j, long long i) {
+  const bool up2 = j.kind == B200GAN_PACK_TC_FPROP_UP2 || j.kind == B200GAN_PACK_TC_DGRAD_UP2;
+  // order 0: dst[t][ci][co], order 1: dst[t][co][ci]
+  const int order = (j.kind == B200GAN_PACK_SIMT_DGRAD || j.kind == B200GAN_PACK_TC_FPROP || j.kind == B200GAN_PACK_TC_FPROP_UP2) ? 1 : 0;
+  int ci, co;
+  long long t;
+  if (order == 0) { co = (int)(i % j.Cout); t = i / j.Cout; ci = (int)(t % j.Cin); t /= j.Cin; }
+  else            { ci = (int)(i % j.Cin);  t = i / j.Cin;  co = (int)(t % j.Cout); t /= j.Cout; }
+  if (!up2) {
+    const int s = (int)(t % j.S), r = (int)(t / j.S);
+    const long long si = j.transposed ? (((long long)ci * j.Cout + co) * j.R + r) * j.S + s
+                                      : (((long long)co * j.Cin + ci) * j.R + r) * j.S + s;
+    const float v = j.src[si];
+    return (j.kind == B200GAN_PACK_TC_FPROP || j.kind == B200GAN_PACK_TC_DGRAD) ? round_tf32(v) : v;
+  }
+  const int tap = (int)(t % 4), ph = (int)(t / 4);
+  const int a = ph >> 1, b = ph & 1, dr = tap >> 1, ds = tap & 1;
+  int rlo, rhi, slo, shi;
+  up2_rset(a, dr, rlo, rhi);
+  up2_rset(b, ds, slo, shi);
+  float v = 0.f;
+  for (int r = rlo; r <= rhi; ++r)
+    for (int s = slo; s <= shi; ++s) v += j.src[(((long long)co * j.Cin + ci) * 3 + r) * 3 + s];
+  return round_tf32(v);
+}
+__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackTable tb) {
+  int lo = 0, hi = tb.count;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tb.block_begin[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const PackJob &j = tb.job[lo];
+  const long long i0 = (long long)((int)blockIdx.x - tb.block_begin[lo]) * PACK_CHUNK;
+  long long i1 = i0 + PACK_CHUNK;
+  if (i1 > j.total) i1 = j.total;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) j.dst[i] = pack_element(j, i);
+}
+
 }  // namespace b200gan
 
 using namespace b200gan;
+
+extern "C" int b200gan_pack_weights_multi(const b200gan_pack_job *jobs, int32_t count, void *stream) {
+  B2_CHECK_ARG(count >= 0 && (count == 0 || jobs != nullptr), "pack_weights_multi: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  for (int base = 0; base < count; base += PACK_MAX_JOBS) {
+    PackTable tb;
+    const int c = count - base < PACK_MAX_JOBS ? count - base : PACK_MAX_JOBS;
+    int blocks = 0;
+    for (int i = 0; i < c; ++i) {
+      const b200gan_pack_job &jb = jobs[base + i];
+      if (int e = validate_geom(&jb.geom)) return e;
+      B2_CHECK_ARG(jb.w && jb.packed, "pack_weights_multi: job %d has a null pointer", base + i);
+      B2_CHECK_ARG(jb.pack >= B200GAN_PACK_SIMT_FPROP && jb.pack <= B200GAN_PACK_TC_DGRAD_UP2, "pack_weights_multi: pack id");
+      const bool up2 = jb.pack == B200GAN_PACK_TC_FPROP_UP2 || jb.pack == B200GAN_PACK_TC_DGRAD_UP2;
+      if (up2)
+        B2_CHECK_ARG(!jb.geom.transposed && jb.geom.up == 2 && jb.geom.R == 3 && jb.geom.S == 3,
+                     "pack_weights_multi: UP2 fold needs a 3x3 conv behind a x2 upsample");
+      PackJob &j = tb.job[i];
+      j.src = jb.w; j.dst = jb.packed;
+      j.R = jb.geom.R; j.S = jb.geom.S; j.Cin = jb.geom.C; j.Cout = jb.geom.K; j.transposed = jb.geom.transposed;
+      j.kind = jb.pack;
+      j.total = (long long)b200gan_packed_weight_floats(&jb.geom, jb.pack);
+      tb.block_begin[i] = blocks;
+      blocks += (int)ceil_div64(j.total, PACK_CHUNK);
+    }
+    tb.block_begin[c] = blocks;
+    tb.count = c;
+    if (blocks > 0) {
+      pack_multi_kernel<<<(unsigned)blocks, 256, 0, st>>>(tb);
+      B2_LAUNCH_CHECK();
+    }
+  }
+  return B200GAN_OK;
+}
 
 extern "C" int b200gan_version(void) { return B200GAN_VERSION; }
 extern "C" const char *b200gan_last_error(void) { return g_err; }
