@@ -273,6 +273,51 @@ int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, d
                       double beta1, double beta2, double eps, float grad_scale, float *step,
                       void *stream);
 
+/* ---- Discriminator conv blocks as a fused chain (csrc/narrow_block.cu) -------------------------------------------- */
+/* Replaces, for the narrow strided layers of dcgan.py:77-88
+ *     [nn.Conv2d(in, out, 3, 2, 1), nn.LeakyReLU(0.2, inplace=True), nn.Dropout2d(0.25), nn.BatchNorm2d(out, 0.8)] x 4
+ * every kernel between two convolutions: a layer stores a_l = dropout(lrelu(conv_l(x_l) + b_l)) and the batch sums of
+ * a_l; the normalised tensor x_{l+1} = BN_l(a_l) is applied while the consumer gathers its operands and is never
+ * written.  A BatchNorm seen from these kernels is the raw batch statistics plus its parameters: */
+typedef struct b200gan_nb_bn {
+  const double *stats; /* [2][C] sum, sum of squares of the normalised tensor over N*H*W; NULL = no BatchNorm */
+  const float *gamma;  /* [C] or NULL (= 1) */
+  const float *beta;   /* [C] or NULL (= 0) */
+  float eps;
+  double count;        /* N*H*W */
+} b200gan_nb_bn;
+/* 1 if the geometry can run in the fused chain (Conv2d, zero padding, stride 1/2, 3x3 or 4x4, C <= 128 (1 or a
+ * multiple of 4), K a power of two in [4, 128]) */
+int b200gan_nb_supported(const b200gan_conv_geom *g);
+/* y = chan_scale[n,k] * act(conv(BN_in(x)) + bias): x = a_{l-1} [N][H][W][C]; packed = B200GAN_PACK_SIMT_FPROP.
+ * in_bn (may be NULL): the BatchNorm between the producer and this conv, finalised in the prologue; running_mean/var and
+ * num_batches_tracked (may be NULL) are updated once per call with torch semantics.  out_stats [2][K] (may be NULL):
+ * OVERWRITTEN with the batch sums of y for the next BatchNorm. */
+int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, float *running_mean, float *running_var,
+                     int64_t *num_batches_tracked, float momentum, const float *x, const float *packed,
+                     const float *bias, int32_t act, float slope, const float *chan_scale, float *y,
+                     double *out_stats, void *stream);
+/* dz = BN_out-backward(g) * chan_scale * act'(a) and db[K] = column sums of dz (may be NULL).  g: gradient w.r.t. the
+ * (virtual) BatchNorm output, or w.r.t. a itself when out_bn is NULL; sums [2][K]: sum g, sum g * ahat (complete). */
+int b200gan_nb_dz(int32_t N, int64_t PQ, int32_t K, const float *g, const float *a, const float *chan_scale,
+                  int32_t act, float slope, const b200gan_nb_bn *out_bn, const double *sums, float *dz, float *db,
+                  void *stream);
+/* dw [K][C][R][S] (OVERWRITTEN) from dz [N][P][Q][K] and x = BN_in(a_{l-1}) recomputed on the fly */
+int b200gan_nb_wgrad(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
+                     void *stream);
+/* g_out [N][H][W][C] = gradient w.r.t. the conv's (virtual) input; packed = B200GAN_PACK_SIMT_DGRAD.  With in_bn, a_prev
+ * (= the stored input a_{l-1}) and sums [2][C]: sums is OVERWRITTEN with sum g_out, sum g_out * ahat_prev, which is what
+ * the backward of the BatchNorm in front of this conv needs (and its dbeta / dgamma). */
+int b200gan_nb_dgrad(const b200gan_conv_geom *g, const float *dz, const float *packed, const b200gan_nb_bn *in_bn,
+                     const float *a_prev, float *g_out, double *sums, void *stream);
+/* End of a chain: out = BN(a) as a real tensor, [N][C][HW] (nchw != 0: what the script's .view expects, dcgan.py:96) or
+ * [N][HW][C]; and its backward: g [N][HW][C] = dout re-laid-out, sums [2][C] OVERWRITTEN. */
+int b200gan_nb_tail_fwd(int32_t N, int32_t HW, int32_t C, const b200gan_nb_bn *bn, float *running_mean,
+                        float *running_var, int64_t *num_batches_tracked, float momentum, const float *a, float *out,
+                        int32_t nchw, void *stream);
+int b200gan_nb_tail_bwd(int32_t N, int32_t HW, int32_t C, const b200gan_nb_bn *bn, const float *a, const float *dout,
+                        int32_t nchw, float *g, double *sums, void *stream);
+
 /* ---- Discriminator head and adversarial loss (csrc/head.cu) --------------------------------------------------- */
 /* y[n] = act(dot(x[n], w) + b): nn.Linear(K, 1) [+ nn.Sigmoid]  (dcgan.py:92).  x [N][K] row-major. */
 int b200gan_linear1_fwd(const float *x, const float *w, const float *b, float *y, int32_t N, int32_t K, int32_t act,

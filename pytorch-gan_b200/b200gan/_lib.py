@@ -46,6 +46,10 @@ class PackJob(ctypes.Structure):
     _fields_ = [("w", c_vp), ("packed", c_vp), ("geom", ConvGeom), ("pack", c_i32)]
 
 
+class NbBn(ctypes.Structure):
+    _fields_ = [("stats", c_vp), ("gamma", c_vp), ("beta", c_vp), ("eps", c_f32), ("count", c_f64)]
+
+
 class TailDesc(ctypes.Structure):
     _fields_ = [("N", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32), ("K", c_i32), ("act_mid", c_i32),
                 ("slope", c_f32), ("act_out", c_i32)]
@@ -90,6 +94,14 @@ SIGNATURES = {
     "b200gan_gp_mlp_workspace_floats": (c_sz, [_P(GpMlpDesc)]),
     "b200gan_gp_mlp_fwd_bwd": (c_i32, [_P(GpMlpDesc)] + [c_vp] * 12),
     "b200gan_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f32, c_vp, c_vp]),
+    "b200gan_nb_supported": (c_i32, [_P(ConvGeom)]),
+    "b200gan_nb_fprop": (c_i32, [_P(ConvGeom), _P(NbBn), c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_i32, c_f32, c_vp,
+                                 c_vp, c_vp, c_vp]),
+    "b200gan_nb_dz": (c_i32, [c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_f32, _P(NbBn), c_vp, c_vp, c_vp, c_vp]),
+    "b200gan_nb_wgrad": (c_i32, [_P(ConvGeom), _P(NbBn), c_vp, c_vp, c_vp, c_vp]),
+    "b200gan_nb_dgrad": (c_i32, [_P(ConvGeom), c_vp, c_vp, _P(NbBn), c_vp, c_vp, c_vp, c_vp]),
+    "b200gan_nb_tail_fwd": (c_i32, [c_i32, c_i32, c_i32, _P(NbBn), c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i32, c_vp]),
+    "b200gan_nb_tail_bwd": (c_i32, [c_i32, c_i32, c_i32, _P(NbBn), c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "b200gan_linear1_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "b200gan_linear1_bwd": (c_i32, [c_vp] * 7 + [c_i32, c_i32, c_i32, c_vp]),
     "b200gan_bce_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),

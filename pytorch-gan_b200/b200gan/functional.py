@@ -367,6 +367,97 @@ class ActFn(torch.autograd.Function):
         return ops.epilogue_bwd(dy, y, mask, ctx.act, ctx.slope), None, None, None, None
 
 
+@dataclass(frozen=True)
+class NbSpec:
+    stride: int = 1
+    pad: int = 0
+    act: int = ACT_NONE
+    slope: float = 0.0
+    momentum: float = 0.0     # of the BatchNorm on the INPUT edge (its running statistics are updated by this conv)
+    want_stats: bool = False  # a training-mode BatchNorm follows: produce the batch sums of the output
+
+
+class NbConvFn(torch.autograd.Function):
+    """One layer of a fused narrow chain (csrc/narrow_block.cu): conv over the (virtually normalised) stored output of
+    the previous layer, + bias, activation, Dropout2d scale, + the batch sums for the following BatchNorm.
+
+    Chain protocol.  `in_edge` / `out_edge` are ops.BnEdge objects shared with the neighbouring layers.  In backward the
+    incoming gradient is w.r.t. the VIRTUAL normalised output (the consumer could not finish the BatchNorm backward
+    without the batch sums); by then the consumer has stored those sums in out_edge.sums.  This node finishes the norm
+    backward (nb_dz), computes its parameter gradients, and hands ITS producer a virtual gradient plus in_edge.sums.
+    Only valid when the stored output has exactly one consumer: the next node of the same chain."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, chan_scale, in_gamma, in_beta, in_rm, in_rv, in_nbt, in_edge, out_box, spec, cache):
+        ops._require_cuda(x, "conv input")
+        x = _as_cl(x)
+        g, _ = ops.make_geom(tuple(x.shape), tuple(weight.shape), spec.stride, (spec.pad,) * 4)
+        w = weight.detach()
+        packed = cache.get(g, w, PACK_SIMT_FPROP)
+        y, stats = ops.nb_fprop(g, x, packed, None if bias is None else bias.detach(), spec.act, spec.slope, chan_scale,
+                                in_edge, in_rm, in_rv, in_nbt, spec.momentum, spec.want_stats)
+        ctx.g, ctx.spec, ctx.cache, ctx.in_edge, ctx.out_box = g, spec, cache, in_edge, out_box
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y, chan_scale)
+        if spec.want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy, *unused):
+        x, weight, y, chan_scale = ctx.saved_tensors
+        g, spec, in_edge = ctx.g, ctx.spec, ctx.in_edge
+        out_edge = ctx.out_box[0] if ctx.out_box else None
+        if out_edge is not None and out_edge.sums is None:
+            raise RuntimeError("b200gan: fused conv chain: the consumer of this layer did not run its backward first")
+        gy = _as_cl(gy)
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        dz, db = ops.nb_dz(gy, y, chan_scale, spec.act, spec.slope, out_edge, want_db)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.nb_wgrad(g, x, dz, in_edge, tuple(weight.shape))
+        gx = dgamma = dbeta = None
+        need_in = ctx.needs_input_grad[0] or (in_edge is not None and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5]))
+        if need_in:
+            packed = ctx.cache.get(g, weight.detach(), PACK_SIMT_DGRAD)
+            gx, sums = ops.nb_dgrad(g, dz, packed, in_edge, x)
+            if in_edge is not None:
+                in_edge.sums = sums
+                c = g.C
+                if ctx.needs_input_grad[4]:
+                    dgamma = sums[c:].float()
+                if ctx.needs_input_grad[5]:
+                    dbeta = sums[:c].float()
+        return gx, dw, db, None, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+class NbTailFn(torch.autograd.Function):
+    """End of a fused narrow chain: the last BatchNorm's output as a real tensor (optionally NCHW-contiguous: the layout
+    the script's `.view(N, -1)` needs, dcgan.py:96)."""
+
+    @staticmethod
+    def forward(ctx, a, gamma, beta, rm, rv, nbt, edge, momentum, nchw):
+        a = _as_cl(a)
+        out = ops.nb_tail_fwd(a, edge, rm, rv, nbt, momentum, nchw)
+        ctx.edge, ctx.nchw = edge, nchw
+        ctx.save_for_backward(a)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        (a,) = ctx.saved_tensors
+        dout = dout.contiguous() if ctx.nchw else _as_cl(dout)
+        g, sums = ops.nb_tail_bwd(a, ctx.edge, dout, ctx.nchw)
+        ctx.edge.sums = sums
+        c = a.shape[1]
+        dgamma = sums[c:].float() if ctx.needs_input_grad[1] else None
+        dbeta = sums[:c].float() if ctx.needs_input_grad[2] else None
+        return g, dgamma, dbeta, None, None, None, None, None, None
+
+
 class Linear1Fn(torch.autograd.Function):
     """nn.Linear(K, 1) [+ Sigmoid/Tanh/...] on a 2-D CUDA tensor: the discriminator head (dcgan.py:92)."""
 

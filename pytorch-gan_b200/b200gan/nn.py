@@ -295,6 +295,62 @@ class _TailStep:
         self.norm_step, self.conv_step = norm_step, conv_step
 
 
+class _ChainStep:
+    """A run of narrow [Conv2d -> act -> Dropout2d] (+ BatchNorm2d) blocks (dcgan.py:77-88) executed as the fused chain
+    of csrc/narrow_block.cu when the runtime shapes qualify; `steps` are the ordinary steps it stands for."""
+
+    MAX_MACS = 6.0e8   # per layer: above this the tensor-core path is the better choice
+
+    def __init__(self, steps):
+        self.steps = steps
+        self.layers = []  # (conv step, norm step or None)
+        i = 0
+        while i < len(steps):
+            ns = steps[i + 1] if i + 1 < len(steps) and isinstance(steps[i + 1], _NormStep) else None
+            self.layers.append((steps[i], ns))
+            i += 2 if ns is not None else 1
+
+
+def _chain_conv_candidate(cs):
+    if not isinstance(cs, _ConvStep):
+        return False
+    conv = cs.conv
+    if isinstance(conv, _T["ConvTranspose2d"]) or cs.up != 1 or cs.extra_pads != (0, 0, 0, 0) or cs.pad_mode != PAD_ZERO:
+        return False
+    if cs.act not in (ACT_NONE, ACT_LRELU, ACT_RELU):
+        return False
+    k, c = conv.out_channels, conv.in_channels
+    if not (4 <= k <= 128 and (k & (k - 1)) == 0 and 1 <= c <= 128 and (c == 1 or c % 4 == 0)):
+        return False
+    return tuple(conv.kernel_size) in ((3, 3), (4, 4)) and conv.stride[0] in (1, 2)
+
+
+def _chain_norm_candidate(ns):
+    return isinstance(ns, _NormStep) and isinstance(ns.norm, _T["BatchNorm2d"]) and ns.act == ACT_NONE
+
+
+def _fuse_chains(steps):
+    out, i, n = [], 0, len(steps)
+    while i < n:
+        j, convs = i, 0
+        while j < n and _chain_conv_candidate(steps[j]):
+            convs += 1
+            j += 1
+            if j < n and steps[j - 1].stats is False and _chain_norm_candidate(steps[j]):
+                j += 1
+            elif steps[j - 1].stats is not None:
+                j -= 1          # a norm follows that the chain cannot take: the run ends before this conv
+                convs -= 1
+                break
+        if convs >= 2:
+            out.append(_ChainStep(steps[i:j]))
+            i = j
+        else:
+            out.append(steps[i])
+            i += 1
+    return out
+
+
 def _uses_batch_stats(norm):
     return isinstance(norm, _T["InstanceNorm2d"]) or norm.training or norm.running_mean is None
 
@@ -376,6 +432,7 @@ def _build_plan(mods):
             if (k + 1 < len(steps) and isinstance(steps[k + 1], _NormStep) and s.act == ACT_NONE
                     and s.dropout2d is None):
                 steps[k + 1].rtf_dx = True
+    steps = _fuse_chains(steps)
     # the Generator tail: norm + narrow 3x3 conv as one fused node
     fused, k = [], 0
     while k < len(steps):
@@ -397,6 +454,68 @@ class Sequential(_T["Sequential"]):
             cached = (key, _build_plan(mods))
             self.__dict__["_b200_plan"] = cached
         return cached[1]
+
+    def _run_chain(self, chain, x, nchw_out):
+        """Execute a _ChainStep through the fused kernels, or return None if the runtime shapes do not qualify."""
+        if not ops.Config.fuse_narrow_chain or ops.Config.algo == "simt_generic":
+            return None
+        shape = tuple(x.shape)
+        plan = []
+        for cs, ns in chain.layers:
+            conv = cs.conv
+            if shape[1] != conv.in_channels or not _conv_ok(conv):
+                return None
+            g, oshape = ops.make_geom(shape, tuple(conv.weight.shape), int(conv.stride[0]), (int(conv.padding[0]),) * 4)
+            macs = float(oshape[0]) * oshape[2] * oshape[3] * conv.out_channels * conv.in_channels * g.R * g.S
+            if macs > _ChainStep.MAX_MACS or not ops.nb_supported(g) or oshape[2] * oshape[3] < 1:
+                return None
+            if ns is not None:
+                norm = ns.norm
+                if not (norm.training and norm.num_features == conv.out_channels):
+                    return None
+                if norm.track_running_stats and norm.momentum is None:
+                    return None
+            plan.append((cs, ns, oshape))
+            shape = oshape
+        edge, prev_norm = None, None
+        for cs, ns, oshape in plan:
+            conv = cs.conv
+            scale = None
+            if cs.dropout2d is not None and cs.dropout2d.training and cs.dropout2d.p > 0.0:
+                scale = _dropout2d_scale((x.shape[0], conv.out_channels), cs.dropout2d.p, x.device)
+            gam = bet = rm = rv = nbt = None
+            momentum = 0.0
+            if prev_norm is not None:
+                gam, bet = prev_norm.weight, prev_norm.bias
+                if prev_norm.track_running_stats and prev_norm.running_mean is not None:
+                    rm, rv, nbt = prev_norm.running_mean, prev_norm.running_var, prev_norm.num_batches_tracked
+                    momentum = float(prev_norm.momentum)
+            spec = F.NbSpec(stride=int(conv.stride[0]), pad=int(conv.padding[0]), act=cs.act, slope=cs.slope,
+                            momentum=momentum, want_stats=ns is not None)
+            cache = conv.__dict__.get("_b200_cache")
+            if cache is None:
+                cache = PackCache()
+                conv.__dict__["_b200_cache"] = cache
+            out_box = []
+            res = F.NbConvFn.apply(x, conv.weight, conv.bias, scale, gam, bet, rm, rv, nbt, edge, out_box, spec, cache)
+            if ns is not None:
+                x, stats = res
+                norm = ns.norm
+                edge = ops.BnEdge(stats, None if norm.weight is None else norm.weight.detach(),
+                                  None if norm.bias is None else norm.bias.detach(), norm.eps,
+                                  oshape[0] * oshape[2] * oshape[3])
+                out_box.append(edge)
+                prev_norm = norm
+            else:
+                x, edge, prev_norm = res, None, None
+        if edge is not None:
+            norm = prev_norm
+            rm = rv = nbt = None
+            momentum = 0.0
+            if norm.track_running_stats and norm.running_mean is not None:
+                rm, rv, nbt, momentum = norm.running_mean, norm.running_var, norm.num_batches_tracked, float(norm.momentum)
+            x = F.NbTailFn.apply(x, norm.weight, norm.bias, rm, rv, nbt, edge, momentum, bool(nchw_out))
+        return x
 
     def _forward_2d(self, x):
         """Matrix input (the adv_layer of a discriminator, dcgan.py:92): Linear(K, 1) + activation as one node."""
@@ -430,6 +549,16 @@ class Sequential(_T["Sequential"]):
         queue = list(steps)
         while queue:
             s = queue.pop(0)
+            if isinstance(s, _ChainStep):
+                at_end = not queue
+                res = self._run_chain(s, x, want_contiguous and at_end)
+                if res is None:
+                    queue[0:0] = s.steps
+                else:
+                    x, stats = res, None
+                    if at_end and want_contiguous and x.is_contiguous():
+                        return x
+                continue
             if isinstance(s, _TailStep):
                 ns, cs = s.norm_step, s.conv_step
                 norm, conv = ns.norm, cs.conv

@@ -10,7 +10,8 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ALGO_SIMT, ALGO_TC, PAD_REFLECT, PAD_ZERO, ConvGeom, Epilogue, GpMlpDesc, NormDesc, TailDesc)
+from ._lib import (ACT_NONE, ALGO_SIMT, ALGO_TC, PAD_REFLECT, PAD_ZERO, ConvGeom, Epilogue, GpMlpDesc, NbBn, NormDesc,
+                   TailDesc)
 
 CL = torch.channels_last
 
@@ -24,6 +25,8 @@ class Config:
     contiguous_hw_limit = 64
     # BatchNorm2d -> act -> Conv2d(C, K<=3, 3, 1, 1) -> act as the fused tail kernels (csrc/tail.cu)
     fuse_tail = os.environ.get("B200GAN_FUSE_TAIL", "1") not in ("", "0")
+    # [Conv2d -> LeakyReLU -> Dropout2d -> BatchNorm2d] runs of narrow layers as the fused chain (csrc/narrow_block.cu)
+    fuse_narrow_chain = os.environ.get("B200GAN_FUSE_CHAIN", "1") not in ("", "0")
 
 
 def _stream():
@@ -356,6 +359,88 @@ def act_forward(x, act, slope, mask=None, mask_per_channel=False):
     _lib.check(_lib.load().b200gan_act_fwd(x.data_ptr(), _ptr(mask), int(mask_per_channel), act, slope, x.numel(), c,
                                            h * w, y.data_ptr(), _stream()), "act_fwd")
     return y
+
+
+# ---- Discriminator conv blocks as a fused chain (csrc/narrow_block.cu) ------------------------------------------
+class BnEdge:
+    """A training-mode BatchNorm2d between two fused convs: its batch statistics (fp64 sums of the producer's output)
+    and parameters.  `sums` is filled by the consumer's backward (sum g, sum g * ahat) for the producer's backward."""
+
+    def __init__(self, stats, gamma, beta, eps, count):
+        self.stats, self.gamma, self.beta, self.eps, self.count = stats, gamma, beta, float(eps), float(count)
+        self.sums = None
+
+    def c_struct(self):
+        b = NbBn()
+        b.stats, b.gamma, b.beta = self.stats.data_ptr(), _ptr(self.gamma), _ptr(self.beta)
+        b.eps, b.count = self.eps, self.count
+        return b
+
+
+def nb_supported(g):
+    if not Config.fuse_narrow_chain or not bool(_lib.load().b200gan_nb_supported(ctypes.byref(g))):
+        return False
+    return True
+
+
+def _bn_ref(edge):
+    return ctypes.byref(edge.c_struct()) if edge is not None else None
+
+
+def nb_fprop(g, x, packed, bias, act, slope, chan_scale, in_edge, running_mean, running_var, nbt, momentum, want_stats):
+    y = empty_cl(g.N, g.K, g.P, g.Q, x.device)
+    stats = torch.empty(2 * g.K, device=x.device, dtype=torch.float64) if want_stats else None
+    _lib.check(_lib.load().b200gan_nb_fprop(ctypes.byref(g), _bn_ref(in_edge), _ptr(running_mean), _ptr(running_var),
+                                            _ptr(nbt), float(momentum), x.data_ptr(), packed.data_ptr(), _ptr(bias),
+                                            act, slope, _ptr(chan_scale), y.data_ptr(), _ptr(stats), _stream()), "nb_fprop")
+    return y, stats
+
+
+def nb_dz(g_in, a, chan_scale, act, slope, out_edge, want_db):
+    n, k, p, q = a.shape
+    dz = torch.empty_like(a, memory_format=CL)
+    db = torch.empty(k, device=a.device, dtype=torch.float32) if want_db else None
+    sums = out_edge.sums if out_edge is not None else None
+    _lib.check(_lib.load().b200gan_nb_dz(n, p * q, k, g_in.data_ptr(), a.data_ptr(), _ptr(chan_scale), act, slope,
+                                         _bn_ref(out_edge), _ptr(sums), dz.data_ptr(), _ptr(db), _stream()), "nb_dz")
+    return dz, db
+
+
+def nb_wgrad(g, x, dz, in_edge, weight_shape):
+    dw = torch.empty(weight_shape, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().b200gan_nb_wgrad(ctypes.byref(g), _bn_ref(in_edge), x.data_ptr(), dz.data_ptr(), dw.data_ptr(),
+                                            _stream()), "nb_wgrad")
+    return dw
+
+
+def nb_dgrad(g, dz, packed, in_edge, a_prev):
+    gout = empty_cl(g.N, g.C, g.H, g.W, dz.device)
+    sums = torch.empty(2 * g.C, device=dz.device, dtype=torch.float64) if in_edge is not None else None
+    _lib.check(_lib.load().b200gan_nb_dgrad(ctypes.byref(g), dz.data_ptr(), packed.data_ptr(), _bn_ref(in_edge),
+                                            _ptr(a_prev) if in_edge is not None else 0, gout.data_ptr(), _ptr(sums),
+                                            _stream()), "nb_dgrad")
+    return gout, sums
+
+
+def nb_tail_fwd(a, edge, running_mean, running_var, nbt, momentum, nchw):
+    n, c, h, w = a.shape
+    if nchw:
+        out = torch.empty((n, c, h, w), device=a.device, dtype=torch.float32)
+    else:
+        out = torch.empty_like(a, memory_format=CL)
+    _lib.check(_lib.load().b200gan_nb_tail_fwd(n, h * w, c, _bn_ref(edge), _ptr(running_mean), _ptr(running_var), _ptr(nbt),
+                                               float(momentum), a.data_ptr(), out.data_ptr(), int(nchw), _stream()),
+               "nb_tail_fwd")
+    return out
+
+
+def nb_tail_bwd(a, edge, dout, nchw):
+    n, c, h, w = a.shape
+    g = torch.empty_like(a, memory_format=CL)
+    sums = torch.empty(2 * c, device=a.device, dtype=torch.float64)
+    _lib.check(_lib.load().b200gan_nb_tail_bwd(n, h * w, c, _bn_ref(edge), a.data_ptr(), dout.data_ptr(), int(nchw),
+                                               g.data_ptr(), sums.data_ptr(), _stream()), "nb_tail_bwd")
+    return g, sums
 
 
 # ---- Discriminator head / adversarial loss (csrc/head.cu) ----------------------------------------------------

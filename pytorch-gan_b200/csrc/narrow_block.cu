@@ -1,0 +1,767 @@
+// narrow_block.cu -- the Discriminator's strided conv blocks as a fused chain of fp32 kernels.
+//
+// Reference: dcgan.py:77-88
+//     block = [nn.Conv2d(in, out, 3, 2, 1), nn.LeakyReLU(0.2, inplace=True), nn.Dropout2d(0.25)] (+ nn.BatchNorm2d(out, 0.8))
+//     self.model = nn.Sequential(*block(1, 16, bn=False), *block(16, 32), *block(32, 64), *block(64, 128))
+// At the BASELINE size these four layers move 16 MB per pass and execute 0.94 GFLOP: they are launch- and latency-bound,
+// and un-fused they cost ~15 launches forward and ~35 backward per discriminator pass (conv, epilogue backward, bias
+// gradient, BatchNorm statistics / finalize / apply / backward reduce / backward apply / parameter gradients, ...).
+// Here a layer l keeps only a_l = dropout(lrelu(conv_l(x_l) + b_l)) and the batch sums of a_l in memory; the normalised
+// tensor x_{l+1} = BN_l(a_l) is never written:
+//   nbk_fprop   x_l = a_{l-1} * scale + shift applied while gathering (BatchNorm "apply" of the producer folded into the
+//               consumer's loads; zero padding stays zero), bias + LeakyReLU + Dropout2d scale in registers, the sums
+//               / sums of squares the NEXT BatchNorm needs reduced in the epilogue (warp shuffles -> one fp64 atomic per
+//               channel and block).  The BatchNorm finalisation (mean, rstd, running statistics) happens in the prologue
+//               of the consumer: no finalize / apply kernels at all.
+//   nbk_dz      dz_l = BN_l-backward(G_{l+1}) * dropout scale * lrelu'(a_l), element-wise from the sums the upstream
+//               dgrad accumulated, + the bias gradient.
+//   nbk_wgrad   dW_l from dz_l and x_l (recomputed from a_{l-1} while staging the patch in shared memory); thread =
+//               (input channel, 4 output channels) x all taps in registers, pixels streamed through shared memory.
+//   nbk_dgrad   G_l = transposed gather of dz_l by stride-parity class + the sums BN_{l-1}'s backward needs, in the epilogue.
+//   nbk_tail_*  BN_4 apply fused with the NHWC -> NCHW layout change the script's .view needs (dcgan.py:96), and back.
+// G_l is the gradient w.r.t. the VIRTUAL tensor x_l; the BatchNorm backward is finished by the consumer (nbk_dz of layer
+// l-1) once the sums are complete.  See b200gan/functional.py (NbConvFn, NbTailFn) for the autograd wiring.
+#include "tc_common.cuh"
+#include <string.h>
+
+namespace b200gan {
+
+struct NbBn {
+  const double *stats;  // [2][C]: sum, sum of squares over the batch (null: no BatchNorm on this edge)
+  const float *gamma, *beta;
+  float eps;
+  double count;
+};
+
+__device__ __forceinline__ void nb_bn_consts(const NbBn &bn, int C, int c, float &mean, float &rstd, float &sc,
+                                             float &sh, double *var_out = nullptr) {
+  const double m = bn.stats[c] / bn.count;
+  double var = bn.stats[C + c] / bn.count - m * m;
+  if (var < 0.0) var = 0.0;
+  if (var_out) *var_out = var;
+  rstd = (float)(1.0 / sqrt(var + (double)bn.eps));
+  mean = (float)m;
+  const float ga = bn.gamma ? bn.gamma[c] : 1.f, be = bn.beta ? bn.beta[c] : 0.f;
+  sc = ga * rstd;
+  sh = be - mean * sc;
+}
+
+__device__ __forceinline__ void nb_update_running(const NbBn &bn, int C, int c, float *rm, float *rv, float momentum) {
+  float mean, rstd, sc, sh;
+  double var;
+  nb_bn_consts(bn, C, c, mean, rstd, sc, sh, &var);
+  const double unbiased = bn.count > 1.0 ? var * bn.count / (bn.count - 1.0) : var;
+  rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
+  rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+}
+
+__device__ __forceinline__ float nb_act(float v, int act, float slope) {
+  if (act == B200GAN_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == B200GAN_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+__device__ __forceinline__ float nb_act_grad(float a, int act, float slope) {
+  if (act == B200GAN_ACT_LRELU) return a > 0.f ? 1.f : slope;
+  if (act == B200GAN_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// sum over the 32 lanes of a warp
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int NB_MAXC = 128;
+
+// ---- forward ------------------------------------------------------------------------------------------------------
+struct NbFprop {
+  const float *x, *wp, *bias, *cs;
+  float *y;
+  double *out_stats;
+  NbBn in_bn;
+  float *rm, *rv;
+  long long *nbt;
+  float momentum;
+  int N, H, W, C, P, Q, K, R, S, stride, pad_t, pad_l;
+  float slope;
+  int act;
+  int Mpad;  // output pixels rounded up to a multiple of the block size: every block has ONE channel group
+};
+
+// thread = (channel group kg, output pixel m); kg is uniform per block, lanes are consecutive pixels
+template <int KT>
+__global__ void __launch_bounds__(256)
+nbk_fprop_kernel(const __grid_constant__ NbFprop p) {
+  __shared__ float sc_s[NB_MAXC], sh_s[NB_MAXC];
+  __shared__ float red[8][2 * KT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool has_in = p.in_bn.stats != nullptr;
+  if (has_in && tid < p.C) {
+    float mean, rstd, sc, sh;
+    nb_bn_consts(p.in_bn, p.C, tid, mean, rstd, sc, sh);
+    sc_s[tid] = sc;
+    sh_s[tid] = sh;
+    if (blockIdx.x == 0 && p.rm) nb_update_running(p.in_bn, p.C, tid, p.rm, p.rv, p.momentum);
+  }
+  if (has_in && blockIdx.x == 0 && tid == 0 && p.nbt) *p.nbt += 1;
+  __syncthreads();
+
+  const int64_t M = (int64_t)p.N * p.P * p.Q;
+  const int64_t t = (int64_t)blockIdx.x * 256 + tid;
+  const int kg = (int)(t / p.Mpad);
+  const int64_t m = t % p.Mpad;
+  const bool valid = m < M;
+  const int k0 = kg * KT;
+  float acc[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) acc[j] = 0.f;
+  int n = 0, po = 0, qo = 0;
+  if (valid) {
+    qo = (int)(m % p.Q);
+    const int64_t t2 = m / p.Q;
+    po = (int)(t2 % p.P);
+    n = (int)(t2 / p.P);
+    for (int r = 0; r < p.R; ++r) {
+      const int ih = po * p.stride - p.pad_t + r;
+      if (ih < 0 || ih >= p.H) continue;
+      for (int s = 0; s < p.S; ++s) {
+        const int iw = qo * p.stride - p.pad_l + s;
+        if (iw < 0 || iw >= p.W) continue;
+        const float *xp = p.x + ((int64_t)(n * p.H + ih) * p.W + iw) * p.C;
+        const float *wt = p.wp + (int64_t)(r * p.S + s) * p.C * p.K + k0;
+        if ((p.C & 3) == 0) {
+          for (int c = 0; c < p.C; c += 4) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xp + c));
+            float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            if (has_in) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) xs[j] = fmaf(xs[j], sc_s[c + j], sh_s[c + j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float *wr = wt + (int64_t)(c + j) * p.K;
+#pragma unroll
+              for (int u = 0; u < KT / 4; ++u) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wr + 4 * u));
+                acc[4 * u + 0] = fmaf(xs[j], w4.x, acc[4 * u + 0]);
+                acc[4 * u + 1] = fmaf(xs[j], w4.y, acc[4 * u + 1]);
+                acc[4 * u + 2] = fmaf(xs[j], w4.z, acc[4 * u + 2]);
+                acc[4 * u + 3] = fmaf(xs[j], w4.w, acc[4 * u + 3]);
+              }
+            }
+          }
+        } else {
+          for (int c = 0; c < p.C; ++c) {
+            float xs = __ldg(xp + c);
+            if (has_in) xs = fmaf(xs, sc_s[c], sh_s[c]);
+            const float *wr = wt + (int64_t)c * p.K;
+#pragma unroll
+            for (int u = 0; u < KT / 4; ++u) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wr + 4 * u));
+              acc[4 * u + 0] = fmaf(xs, w4.x, acc[4 * u + 0]);
+              acc[4 * u + 1] = fmaf(xs, w4.y, acc[4 * u + 1]);
+              acc[4 * u + 2] = fmaf(xs, w4.z, acc[4 * u + 2]);
+              acc[4 * u + 3] = fmaf(xs, w4.w, acc[4 * u + 3]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      float v = acc[j];
+      if (p.bias) v += __ldg(p.bias + k0 + j);
+      v = nb_act(v, p.act, p.slope);
+      if (p.cs) v *= __ldg(p.cs + (int64_t)n * p.K + k0 + j);
+      acc[j] = v;
+    }
+    float *yo = p.y + m * p.K + k0;
+#pragma unroll
+    for (int u = 0; u < KT / 4; ++u)
+      *reinterpret_cast<float4 *>(yo + 4 * u) = make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+  }
+  if (p.out_stats) {
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float v = valid ? acc[j] : 0.f;
+      const float s1 = warp_sum(v), s2 = warp_sum(v * v);
+      if (lane == 0) {
+        red[warp][j] = s1;
+        red[warp][KT + j] = s2;
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * KT) {
+      float tsum = 0.f;
+#pragma unroll
+      for (int wi = 0; wi < 8; ++wi) tsum += red[wi][tid];
+      const int j = tid % KT;
+      atomicAdd(p.out_stats + (tid < KT ? 0 : p.K) + k0 + j, (double)tsum);
+    }
+  }
+}
+
+// ---- dz = BatchNorm backward (from complete sums) * Dropout2d scale * act'(a), + bias gradient ---------------------------
+struct NbDz {
+  const float *g, *a, *cs;
+  float *dz, *db;
+  NbBn out_bn;
+  const double *sums;  // [2][K]: sum G, sum G * ahat (null with out_bn.stats == null)
+  int64_t rows;        // N * P * Q
+  int64_t PQ;
+  int K;
+  float slope;
+  int act;
+};
+__global__ void __launch_bounds__(256)
+nbk_dz_kernel(const __grid_constant__ NbDz p) {
+  __shared__ float red[256][4];
+  const int tid = threadIdx.x;
+  const int K4 = p.K >> 2;              // 256 % K4 == 0 (checked by the launcher)
+  const int kq = tid % K4;
+  const int rows_per_block = 256 / K4;
+  const bool has_bn = p.out_bn.stats != nullptr;
+  float mean[4], rstd[4], sc[4], m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mean[j] = 0.f; rstd[j] = 0.f; sc[j] = 1.f; m1[j] = 0.f; m2[j] = 0.f;
+    if (has_bn) {
+      float sh;
+      nb_bn_consts(p.out_bn, p.K, kq * 4 + j, mean[j], rstd[j], sc[j], sh);
+      m1[j] = (float)(p.sums[kq * 4 + j] / p.out_bn.count);
+      m2[j] = (float)(p.sums[p.K + kq * 4 + j] / p.out_bn.count);
+    }
+  }
+  float dbs[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + tid / K4; row < p.rows;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t off = row * p.K + kq * 4;
+    const float4 gv = __ldg(reinterpret_cast<const float4 *>(p.g + off));
+    const float4 av = __ldg(reinterpret_cast<const float4 *>(p.a + off));
+    const float G[4] = {gv.x, gv.y, gv.z, gv.w}, A[4] = {av.x, av.y, av.z, av.w};
+    float csv[4] = {1.f, 1.f, 1.f, 1.f};
+    if (p.cs) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4 *>(p.cs + (row / p.PQ) * p.K + kq * 4));
+      csv[0] = c4.x; csv[1] = c4.y; csv[2] = c4.z; csv[3] = c4.w;
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float dA = G[j];
+      if (has_bn) dA = sc[j] * (G[j] - m1[j] - ((A[j] - mean[j]) * rstd[j]) * m2[j]);
+      o[j] = dA * csv[j] * nb_act_grad(A[j], p.act, p.slope);
+      dbs[j] += o[j];
+    }
+    *reinterpret_cast<float4 *>(p.dz + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (p.db) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[tid][j] = dbs[j];
+    __syncthreads();
+    if (tid < K4) {
+      float t4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < rows_per_block; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t4[j] += red[r * K4 + tid][j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(p.db + tid * 4 + j, t4[j]);
+    }
+  }
+}
+
+// ---- weight gradient ---------------------------------------------------------------------------------------------------
+struct NbWgrad {
+  const float *x, *dz;
+  float *dw;
+  NbBn in_bn;
+  int N, H, W, C, P, Q, K, R, S, stride, pad_t, pad_l;
+  int TR, TQ, tiles_r, tiles_q;  // output-pixel tile and tiles per image
+  int PR, PC;                    // patch rows / columns = (TR-1)*stride + R, (TQ-1)*stride + S
+  int SPB, PS;                   // sets per block (<= 256), pixel split = 256 / SPB
+  int nsets;                     // C * K/4
+};
+// thread = set (c, kg: 4 output channels) x all TAPS taps in registers, and one of PS pixel phases.
+// grid = (persistent blocks over tiles, set chunks).  dynamic smem: patch [PR][PC][C] | dz tile [TR*TQ][K] | sc, sh [C]
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
+  extern __shared__ __align__(16) float nsm[];
+  float *x_s = nsm;
+  float *dz_s = x_s + ((p.PR * p.PC * p.C + 3) & ~3);
+  float *sc_s = dz_s + p.TR * p.TQ * p.K;
+  float *sh_s = sc_s + p.C;
+  const int tid = threadIdx.x;
+  const bool has_in = p.in_bn.stats != nullptr;
+  if (tid < p.C) {
+    float mean, rstd, sc = 1.f, sh = 0.f;
+    if (has_in) nb_bn_consts(p.in_bn, p.C, tid, mean, rstd, sc, sh);
+    sc_s[tid] = sc;
+    sh_s[tid] = sh;
+  }
+  const int set_local = tid % p.SPB, psplit = tid / p.SPB;
+  const int set = blockIdx.y * p.SPB + set_local;
+  const bool set_ok = set < p.nsets;
+  const int c = set_ok ? set % p.C : 0, kg = set_ok ? set / p.C : 0;
+  float acc[TAPS][4];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  const int ntiles = p.N * p.tiles_r * p.tiles_q;
+  const int tile_px = p.TR * p.TQ;
+  int toff[TAPS];  // offset of tap t inside the patch, relative to the pixel's top-left element
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) toff[t] = ((t / p.S) * p.PC + (t % p.S)) * p.C;
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tq = tile % p.tiles_q;
+    const int tr = (tile / p.tiles_q) % p.tiles_r;
+    const int n = tile / (p.tiles_q * p.tiles_r);
+    const int p0 = tr * p.TR, q0 = tq * p.TQ;
+    // patch of x_l = a_{l-1} * scale + shift (zero outside the image: the conv's zero padding comes after the norm)
+    const int h0 = p0 * p.stride - p.pad_t, w0 = q0 * p.stride - p.pad_l;
+    for (int i = tid; i < p.PR * p.PC * p.C; i += 256) {
+      const int cc = i % p.C;
+      const int pc = (i / p.C) % p.PC;
+      const int pr = i / (p.C * p.PC);
+      const int ih = h0 + pr, iw = w0 + pc;
+      float v = 0.f;
+      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+        v = fmaf(__ldg(p.x + ((int64_t)(n * p.H + ih) * p.W + iw) * p.C + cc), sc_s[cc], sh_s[cc]);
+      x_s[i] = v;
+    }
+    const int K4 = p.K >> 2;
+    for (int i = tid; i < tile_px * K4; i += 256) {
+      const int k4 = i % K4, pix = i / K4;
+      const int lr = pix / p.TQ, lq = pix % p.TQ;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p0 + lr < p.P && q0 + lq < p.Q)
+        v = __ldg(reinterpret_cast<const float4 *>(p.dz + ((int64_t)(n * p.P + p0 + lr) * p.Q + q0 + lq) * p.K) + k4);
+      reinterpret_cast<float4 *>(dz_s)[i] = v;
+    }
+    __syncthreads();
+    if (set_ok) {
+      for (int pix = psplit; pix < tile_px; pix += p.PS) {
+        const int lr = pix / p.TQ, lq = pix % p.TQ;
+        const float4 d4 = *reinterpret_cast<const float4 *>(dz_s + pix * p.K + kg * 4);
+        const float *xb = x_s + ((lr * p.stride) * p.PC + lq * p.stride) * p.C + c;
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+          const float xv = xb[toff[t]];
+          acc[t][0] = fmaf(xv, d4.x, acc[t][0]);
+          acc[t][1] = fmaf(xv, d4.y, acc[t][1]);
+          acc[t][2] = fmaf(xv, d4.z, acc[t][2]);
+          acc[t][3] = fmaf(xv, d4.w, acc[t][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // dw[k][c][r][s] (parameter layout) += this block's partial sums; pixel phases of one set hit the same addresses
+  if (set_ok) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float *dst = p.dw + ((int64_t)(kg * 4 + j) * p.C + c) * TAPS;
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) atomicAdd(dst + t, acc[t][j]);
+    }
+  }
+}
+
+// ---- data gradient + the sums of the upstream BatchNorm's backward ----------------------------------------------------------
+struct NbDgrad {
+  const float *dz, *wp, *a_prev;
+  float *g_out;
+  double *sums;  // [2][C] (null: no BatchNorm in front of this layer)
+  NbBn in_bn;
+  int N, H, W, C, P, Q, K, R, S, stride, pad_t, pad_l;
+  int Mpad;      // pixels of the largest parity class rounded up to the block size
+};
+// G[n][h][w][c] = sum_{r,s,k} dz[n][(h + pad - r)/stride][(w + pad - s)/stride][k] * w[r][s][k][c] where the division is
+// exact.  blockIdx.z = stride-parity class of (h, w): all pixels of a class use the same taps.  wp: [tap][K][C].
+template <int KT>
+__global__ void __launch_bounds__(256)
+nbk_dgrad_kernel(const __grid_constant__ NbDgrad p) {
+  __shared__ float mean_s[NB_MAXC], rstd_s[NB_MAXC];
+  __shared__ float red[8][2 * KT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool has_in = p.sums != nullptr;
+  if (has_in && tid < p.C) {
+    float sc, sh;
+    nb_bn_consts(p.in_bn, p.C, tid, mean_s[tid], rstd_s[tid], sc, sh);
+  }
+  __syncthreads();
+  const int st = p.stride;
+  const int cls = blockIdx.z;
+  const int pa = cls / st, pb = cls % st;               // first row / column of the class
+  const int r0 = (pa + p.pad_t) % st, s0 = (pb + p.pad_l) % st;
+  const int Rc = r0 < p.R ? (p.R - r0 + st - 1) / st : 0, Sc = s0 < p.S ? (p.S - s0 + st - 1) / st : 0;
+  const int Hc = pa < p.H ? (p.H - pa + st - 1) / st : 0, Wc = pb < p.W ? (p.W - pb + st - 1) / st : 0;
+  const int64_t Mc = (int64_t)p.N * Hc * Wc;
+  const int64_t t = (int64_t)blockIdx.x * 256 + tid;
+  const int cg = (int)(t / p.Mpad);
+  const int64_t m = t % p.Mpad;
+  const bool valid = m < Mc;
+  const int c0 = cg * KT;
+  float acc[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) acc[j] = 0.f;
+  int64_t opix = 0;
+  if (valid) {
+    const int w = pb + st * (int)(m % Wc);
+    const int64_t t2 = m / Wc;
+    const int h = pa + st * (int)(t2 % Hc);
+    const int n = (int)(t2 / Hc);
+    opix = (int64_t)(n * p.H + h) * p.W + w;
+    for (int ir = 0; ir < Rc; ++ir) {
+      const int r = r0 + st * ir;
+      const int th = h + p.pad_t - r;
+      if (th < 0) continue;
+      const int ph = th / st;
+      if (ph >= p.P) continue;
+      for (int is = 0; is < Sc; ++is) {
+        const int s = s0 + st * is;
+        const int tw = w + p.pad_l - s;
+        if (tw < 0) continue;
+        const int pw = tw / st;
+        if (pw >= p.Q) continue;
+        const float *dp = p.dz + ((int64_t)(n * p.P + ph) * p.Q + pw) * p.K;
+        const float *wt = p.wp + (int64_t)(r * p.S + s) * p.K * p.C + c0;
+        for (int k = 0; k < p.K; k += 4) {
+          const float4 dv = __ldg(reinterpret_cast<const float4 *>(dp + k));
+          const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float *wr = wt + (int64_t)(k + j) * p.C;
+            if (KT % 4 == 0) {
+#pragma unroll
+              for (int u = 0; u < KT / 4; ++u) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wr + 4 * u));
+                acc[4 * u + 0] = fmaf(ds[j], w4.x, acc[4 * u + 0]);
+                acc[4 * u + 1] = fmaf(ds[j], w4.y, acc[4 * u + 1]);
+                acc[4 * u + 2] = fmaf(ds[j], w4.z, acc[4 * u + 2]);
+                acc[4 * u + 3] = fmaf(ds[j], w4.w, acc[4 * u + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < KT; ++u) acc[u] = fmaf(ds[j], __ldg(wr + u), acc[u]);
+            }
+          }
+        }
+      }
+    }
+    float *go = p.g_out + opix * p.C + c0;
+    if (KT % 4 == 0) {
+#pragma unroll
+      for (int u = 0; u < KT / 4; ++u)
+        *reinterpret_cast<float4 *>(go + 4 * u) = make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < KT; ++j) go[j] = acc[j];
+    }
+  }
+  if (has_in) {
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      float g = 0.f, gx = 0.f;
+      if (valid) {
+        const float ah = (__ldg(p.a_prev + opix * p.C + c0 + j) - mean_s[c0 + j]) * rstd_s[c0 + j];
+        g = acc[j];
+        gx = acc[j] * ah;
+      }
+      const float s1 = warp_sum(g), s2 = warp_sum(gx);
+      if (lane == 0) {
+        red[warp][j] = s1;
+        red[warp][KT + j] = s2;
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * KT) {
+      float tsum = 0.f;
+#pragma unroll
+      for (int wi = 0; wi < 8; ++wi) tsum += red[wi][tid];
+      atomicAdd(p.sums + (tid < KT ? 0 : p.C) + c0 + (tid % KT), (double)tsum);
+    }
+  }
+}
+
+// ---- tail: BatchNorm apply (+ layout) forward, layout + sums backward ----------------------------------------------------------
+struct NbTail {
+  const float *a;      // [N][HW][C]
+  const float *dout;   // backward: gradient of the output (layout `nchw`)
+  float *out;          // forward: [N][C][HW] (nchw) or [N][HW][C]
+  float *g;            // backward: [N][HW][C]
+  double *sums;        // backward: [2][C]
+  NbBn bn;
+  float *rm, *rv;
+  long long *nbt;
+  float momentum;
+  int N, HW, C, nchw;
+};
+__global__ void __launch_bounds__(256)
+nbk_tail_fwd_kernel(const __grid_constant__ NbTail p) {
+  __shared__ float sc_s[NB_MAXC], sh_s[NB_MAXC];
+  const int tid = threadIdx.x;
+  if (tid < p.C) {
+    float mean, rstd;
+    nb_bn_consts(p.bn, p.C, tid, mean, rstd, sc_s[tid], sh_s[tid]);
+    if (blockIdx.x == 0 && p.rm) nb_update_running(p.bn, p.C, tid, p.rm, p.rv, p.momentum);
+  }
+  if (blockIdx.x == 0 && tid == 0 && p.nbt) *p.nbt += 1;
+  __syncthreads();
+  const int64_t total = (int64_t)p.N * p.HW * p.C;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < total; i += (int64_t)gridDim.x * 256) {
+    int c;
+    int64_t src;
+    if (p.nchw) {  // i enumerates the OUTPUT [n][c][hw]
+      const int hw = (int)(i % p.HW);
+      c = (int)((i / p.HW) % p.C);
+      const int64_t n = i / ((int64_t)p.HW * p.C);
+      src = (n * p.HW + hw) * p.C + c;
+    } else {
+      c = (int)(i % p.C);
+      src = i;
+    }
+    p.out[i] = fmaf(__ldg(p.a + src), sc_s[c], sh_s[c]);
+  }
+}
+// total threads of the grid are a multiple of C, so a thread keeps ONE channel over its grid-stride loop
+__global__ void __launch_bounds__(256)
+nbk_tail_bwd_kernel(const __grid_constant__ NbTail p) {
+  __shared__ float mean_s[NB_MAXC], rstd_s[NB_MAXC];
+  __shared__ float red[256][2];
+  const int tid = threadIdx.x;
+  if (tid < p.C) {
+    float sc, sh;
+    nb_bn_consts(p.bn, p.C, tid, mean_s[tid], rstd_s[tid], sc, sh);
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)p.N * p.HW * p.C;
+  const int c = (int)(((int64_t)blockIdx.x * 256 + tid) % p.C);
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < total; i += (int64_t)gridDim.x * 256) {
+    int64_t src = i;   // i enumerates g [n][hw][c]
+    if (p.nchw) {
+      const int64_t row = i / p.C;
+      const int hw = (int)(row % p.HW);
+      const int64_t n = row / p.HW;
+      src = (n * p.C + c) * p.HW + hw;
+    }
+    const float gv = __ldg(p.dout + src);
+    p.g[i] = gv;
+    const float ah = (__ldg(p.a + i) - mean_s[c]) * rstd_s[c];
+    s1 += gv;
+    s2 = fmaf(gv, ah, s2);
+  }
+  red[tid][0] = s1;
+  red[tid][1] = s2;
+  __syncthreads();
+  if (tid < p.C && tid < 256) {   // 256 % C == 0 or C % 256 == 0 (C <= 128 here): thread `tid` owns channel (block offset + tid) % C
+    float t1 = 0.f, t2 = 0.f;
+    for (int j = tid; j < 256; j += p.C) {
+      t1 += red[j][0];
+      t2 += red[j][1];
+    }
+    const int ch = (int)(((int64_t)blockIdx.x * 256 + tid) % p.C);
+    atomicAdd(p.sums + ch, (double)t1);
+    atomicAdd(p.sums + p.C + ch, (double)t2);
+  }
+}
+
+static NbBn to_bn(const b200gan_nb_bn *b) {
+  NbBn r;
+  r.stats = b ? b->stats : nullptr;
+  r.gamma = b ? b->gamma : nullptr;
+  r.beta = b ? b->beta : nullptr;
+  r.eps = b ? b->eps : 0.f;
+  r.count = b ? b->count : 1.0;
+  return r;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace b200gan
+
+using namespace b200gan;
+
+// geometry the fused chain takes: Conv2d, zero padding, no folded upsample, stride 1 or 2, <= 128 channels either side,
+// K a power of two >= 4 (the channel-group mappings above), fp32 SIMT.
+extern "C" int b200gan_nb_supported(const b200gan_conv_geom *g) {
+  if (!g || validate_geom(g) != B200GAN_OK) return 0;
+  if (g->transposed || g->up != 1 || g->pad_mode != B200GAN_PAD_ZERO) return 0;
+  if (g->stride != 1 && g->stride != 2) return 0;
+  if (g->pad_t != g->pad_b || g->pad_l != g->pad_r) return 0;
+  if (g->C < 1 || g->C > NB_MAXC || g->K < 4 || g->K > NB_MAXC || !is_pow2(g->K)) return 0;
+  if (g->C > 1 && (g->C % 4 != 0)) return 0;
+  if (g->R * g->S != 9 && g->R * g->S != 16) return 0;
+  if ((int64_t)g->R * g->S * g->C * g->K * 4 > (int64_t)512 * 1024) return 0;
+  return 1;
+}
+
+extern "C" int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, float *running_mean,
+                                float *running_var, int64_t *num_batches_tracked, float momentum, const float *x,
+                                const float *packed, const float *bias, int32_t act, float slope, const float *chan_scale,
+                                float *y, double *out_stats, void *stream) {
+  B2_CHECK_ARG(b200gan_nb_supported(g), "nb_fprop: unsupported geometry");
+  B2_CHECK_ARG(x && packed && y, "nb_fprop: null pointer");
+  B2_CHECK_ARG((((uintptr_t)x | (uintptr_t)packed | (uintptr_t)y) & 15) == 0, "nb_fprop: pointers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  if (out_stats) B2_CUDA(cudaMemsetAsync(out_stats, 0, (size_t)2 * g->K * sizeof(double), st));
+  const int64_t M = (int64_t)g->N * g->P * g->Q;
+  if (M == 0) return B200GAN_OK;
+  NbFprop p;
+  p.x = x; p.wp = packed; p.bias = bias; p.cs = chan_scale; p.y = y; p.out_stats = out_stats;
+  p.in_bn = to_bn(in_bn);
+  p.rm = running_mean; p.rv = running_var; p.nbt = reinterpret_cast<long long *>(num_batches_tracked); p.momentum = momentum;
+  p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
+  p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l; p.slope = slope; p.act = act;
+  // more channel groups (KT = 4) when the layer has few pixels, so that the grid still fills the machine
+  const int KT = (g->K % 8 == 0 && M * (g->K / 8) >= 148 * 512) ? 8 : 4;
+  p.Mpad = (int)(ceil_div64(M, 256) * 256);
+  const unsigned blocks = (unsigned)((int64_t)(g->K / KT) * (p.Mpad / 256));
+  if (KT == 8) nbk_fprop_kernel<8><<<blocks, 256, 0, st>>>(p);
+  else nbk_fprop_kernel<4><<<blocks, 256, 0, st>>>(p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_nb_dz(int32_t N, int64_t PQ, int32_t K, const float *g, const float *a, const float *chan_scale,
+                             int32_t act, float slope, const b200gan_nb_bn *out_bn, const double *sums, float *dz, float *db,
+                             void *stream) {
+  B2_CHECK_ARG(g && a && dz && N > 0 && PQ > 0, "nb_dz: bad arguments");
+  B2_CHECK_ARG(K >= 4 && K <= NB_MAXC && is_pow2(K), "nb_dz: K must be a power of two in [4, 128]");
+  B2_CHECK_ARG(!(out_bn && out_bn->stats) || sums, "nb_dz: BatchNorm backward needs the sums");
+  cudaStream_t st = as_stream(stream);
+  if (db) B2_CUDA(cudaMemsetAsync(db, 0, (size_t)K * sizeof(float), st));
+  NbDz p;
+  p.g = g; p.a = a; p.cs = chan_scale; p.dz = dz; p.db = db; p.out_bn = to_bn(out_bn); p.sums = sums;
+  p.rows = (int64_t)N * PQ; p.PQ = PQ; p.K = K; p.slope = slope; p.act = act;
+  const int rows_per_block = 256 / (K / 4);
+  int64_t blocks = ceil_div64(p.rows, rows_per_block * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  nbk_dz_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_nb_wgrad(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz,
+                                float *dw, void *stream) {
+  B2_CHECK_ARG(b200gan_nb_supported(g), "nb_wgrad: unsupported geometry");
+  B2_CHECK_ARG(x && dz && dw, "nb_wgrad: null pointer");
+  cudaStream_t st = as_stream(stream);
+  B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)g->K * g->C * g->R * g->S * sizeof(float), st));
+  if ((int64_t)g->N * g->P * g->Q == 0) return B200GAN_OK;
+  NbWgrad p;
+  p.x = x; p.dz = dz; p.dw = dw; p.in_bn = to_bn(in_bn);
+  p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
+  p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l;
+  // output tile: up to 128 pixels, whole rows when the map is narrow; the patch must fit in shared memory
+  p.TQ = g->Q < 32 ? g->Q : 32;
+  p.TR = 128 / p.TQ;
+  if (p.TR > g->P) p.TR = g->P;
+  auto smem_bytes = [&](int TR, int TQ) {
+    const int PR = (TR - 1) * g->stride + g->R, PC = (TQ - 1) * g->stride + g->S;
+    return (size_t)(((PR * PC * g->C + 3) & ~3) + TR * TQ * g->K + 2 * g->C) * sizeof(float);
+  };
+  while (p.TR > 1 && smem_bytes(p.TR, p.TQ) > 96 * 1024) p.TR = (p.TR + 1) / 2;
+  while (p.TQ > 1 && smem_bytes(p.TR, p.TQ) > 96 * 1024) p.TQ = (p.TQ + 1) / 2;
+  const size_t smem = smem_bytes(p.TR, p.TQ);
+  B2_CHECK_ARG(smem <= 96 * 1024, "nb_wgrad: tile does not fit in shared memory");
+  p.tiles_r = ceil_div(g->P, p.TR);
+  p.tiles_q = ceil_div(g->Q, p.TQ);
+  p.PR = (p.TR - 1) * g->stride + g->R;
+  p.PC = (p.TQ - 1) * g->stride + g->S;
+  p.nsets = g->C * (g->K / 4);
+  int spb = 256;
+  if (p.nsets < 256) {  // fewer sets than threads: several threads share a set and split the pixels of a tile
+    spb = 1;
+    while (spb * 2 <= p.nsets) spb *= 2;
+    if (spb < p.nsets) spb *= 2;        // smallest power of two >= nsets (256 % spb == 0)
+  }
+  p.SPB = spb;
+  p.PS = 256 / spb;
+  const int nchunks = ceil_div(p.nsets, spb);
+  const int ntiles = g->N * p.tiles_r * p.tiles_q;
+  int gx = (2 * 148) / nchunks;
+  if (gx < 8) gx = 8;
+  if (gx > ntiles) gx = ntiles;
+  const int taps = g->R * g->S;
+  static std::atomic<uint64_t> done9{0}, done16{0};
+  dim3 grid((unsigned)gx, (unsigned)nchunks);
+  if (taps == 9) {
+    if (int e = ensure_dynamic_smem(nbk_wgrad_kernel<9>, 96 * 1024, done9)) return e;
+    nbk_wgrad_kernel<9><<<grid, 256, smem, st>>>(p);
+  } else {
+    if (int e = ensure_dynamic_smem(nbk_wgrad_kernel<16>, 96 * 1024, done16)) return e;
+    nbk_wgrad_kernel<16><<<grid, 256, smem, st>>>(p);
+  }
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_nb_dgrad(const b200gan_conv_geom *g, const float *dz, const float *packed,
+                                const b200gan_nb_bn *in_bn, const float *a_prev, float *g_out, double *sums,
+                                void *stream) {
+  B2_CHECK_ARG(b200gan_nb_supported(g), "nb_dgrad: unsupported geometry");
+  B2_CHECK_ARG(dz && packed && g_out, "nb_dgrad: null pointer");
+  B2_CHECK_ARG(!sums || (in_bn && in_bn->stats && a_prev), "nb_dgrad: sums need the upstream BatchNorm and its input");
+  cudaStream_t st = as_stream(stream);
+  if (sums) B2_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * g->C * sizeof(double), st));
+  if ((int64_t)g->N * g->H * g->W == 0) return B200GAN_OK;
+  NbDgrad p;
+  p.dz = dz; p.wp = packed; p.a_prev = a_prev; p.g_out = g_out; p.sums = sums; p.in_bn = to_bn(in_bn);
+  p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
+  p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l;
+  const int st_ = g->stride;
+  const int64_t Mc = (int64_t)g->N * ceil_div(g->H, st_) * ceil_div(g->W, st_);  // class 0 is the largest
+  p.Mpad = (int)(ceil_div64(Mc, 256) * 256);
+  const int KT = g->C % 8 == 0 ? ((Mc * (g->C / 8) * st_ * st_ >= 148 * 512) ? 8 : 4) : (g->C % 4 == 0 ? 4 : 1);
+  dim3 grid((unsigned)((int64_t)(g->C / KT) * (p.Mpad / 256)), 1, (unsigned)(st_ * st_));
+  if (KT == 8) nbk_dgrad_kernel<8><<<grid, 256, 0, st>>>(p);
+  else if (KT == 4) nbk_dgrad_kernel<4><<<grid, 256, 0, st>>>(p);
+  else nbk_dgrad_kernel<1><<<grid, 256, 0, st>>>(p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+static int tail_grid(int64_t total, int C) {
+  int64_t blocks = ceil_div64(total, 256 * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  // total threads a multiple of C (C <= 128 divides 256 when it is a power of two; otherwise round the block count)
+  while ((blocks * 256) % C != 0) ++blocks;
+  return (int)blocks;
+}
+
+extern "C" int b200gan_nb_tail_fwd(int32_t N, int32_t HW, int32_t C, const b200gan_nb_bn *bn, float *running_mean,
+                                   float *running_var, int64_t *num_batches_tracked, float momentum, const float *a,
+                                   float *out, int32_t nchw, void *stream) {
+  B2_CHECK_ARG(bn && bn->stats && a && out && N > 0 && HW > 0 && C > 0 && C <= NB_MAXC, "nb_tail_fwd: bad arguments");
+  NbTail p;
+  memset(&p, 0, sizeof(p));
+  p.a = a; p.out = out; p.bn = to_bn(bn); p.rm = running_mean; p.rv = running_var;
+  p.nbt = reinterpret_cast<long long *>(num_batches_tracked); p.momentum = momentum;
+  p.N = N; p.HW = HW; p.C = C; p.nchw = nchw;
+  nbk_tail_fwd_kernel<<<(unsigned)tail_grid((int64_t)N * HW * C, C), 256, 0, as_stream(stream)>>>(p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+extern "C" int b200gan_nb_tail_bwd(int32_t N, int32_t HW, int32_t C, const b200gan_nb_bn *bn, const float *a,
+                                   const float *dout, int32_t nchw, float *g, double *sums, void *stream) {
+  B2_CHECK_ARG(bn && bn->stats && a && dout && g && sums && N > 0 && HW > 0 && C > 0 && C <= NB_MAXC,
+               "nb_tail_bwd: bad arguments");
+  B2_CHECK_ARG(256 % C == 0, "nb_tail_bwd: C must divide 256");
+  cudaStream_t st = as_stream(stream);
+  B2_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
+  NbTail p;
+  memset(&p, 0, sizeof(p));
+  p.a = a; p.dout = dout; p.g = g; p.sums = sums; p.bn = to_bn(bn);
+  p.N = N; p.HW = HW; p.C = C; p.nchw = nchw;
+  nbk_tail_bwd_kernel<<<(unsigned)tail_grid((int64_t)N * HW * C, C), 256, 0, st>>>(p);
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}

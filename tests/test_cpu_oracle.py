@@ -97,6 +97,8 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.NormDesc) == 9 * 4
     assert ctypes.sizeof(_lib.GpMlpDesc) == 6 * 4
     assert ctypes.sizeof(_lib.TailDesc) == 8 * 4
+    assert ctypes.sizeof(_lib.NbBn) == 40 and ctypes.sizeof(_lib.AdamTensor) == 40
+    assert ctypes.sizeof(_lib.PackJob) == 16 + 17 * 4 + 4
 
 
 def test_geometry_helper_matches_torch_shapes():
@@ -157,11 +159,16 @@ def test_fusion_plan_for_dcgan():
     assert steps[1].stats is False and steps[3].stats is False and steps[3].next_norm is g.conv_blocks[7]
     assert tail.norm_step.takes_stats and tail.norm_step.act == 1 and tail.norm_step.rtf_dx
     assert tail.conv_step.stats is None and tail.conv_step.act == 3
-    dsteps = bnn._build_plan(list(d.model))
+    # the four discriminator blocks (dcgan.py:77-88) form one fused chain; its constituent steps stay available
+    plan = bnn._build_plan(list(d.model))
+    assert [type(s).__name__ for s in plan] == ["_ChainStep"]
+    dsteps = plan[0].steps
     assert [type(s).__name__ for s in dsteps] == ["_ConvStep", "_ConvStep", "_NormStep", "_ConvStep", "_NormStep",
                                                   "_ConvStep", "_NormStep"]
     assert all(s.dropout2d is not None for s in dsteps if isinstance(s, bnn._ConvStep))
     assert dsteps[0].stats is None and dsteps[1].stats is False
+    assert [(type(a).__name__, type(b).__name__) for a, b in plan[0].layers] == [
+        ("_ConvStep", "NoneType"), ("_ConvStep", "_NormStep"), ("_ConvStep", "_NormStep"), ("_ConvStep", "_NormStep")]
 
 
 def test_no_cpu_fallback():
