@@ -187,11 +187,12 @@ int b200gan_norm_finalize(const b200gan_norm_desc *d, double *stats, const float
 /* y = act(x * scale + shift); may run in place (y == x). */
 int b200gan_norm_apply(const b200gan_norm_desc *d, const float *x, const float *scale_shift,
                        float *y, void *stream);
-/* Backward.  Inputs: dy, saved input x, saved output y (only read when act != NONE),
- * mean_rstd, gamma (or NULL).  sums[2][G] fp64 workspace: zero on entry, handed back zeroed.
+/* Backward.  Inputs: dy, saved input x, mean_rstd, gamma (or NULL), and for a fused activation EITHER scale_shift
+ * (LeakyReLU / ReLU: the mask is recomputed from x, nothing else has to be kept) OR the saved output y.
+ * sums[2][G] fp64 workspace: zero on entry, handed back zeroed.
  * Outputs: dx; dgamma_dbeta[2][G] (only meaningful for per_sample == 0 with affine; may be NULL). */
 int b200gan_norm_bwd(const b200gan_norm_desc *d, const float *dy, const float *x, const float *y,
-                     const float *mean_rstd, const float *gamma, double *sums, float *dx,
+                     const float *mean_rstd, const float *scale_shift, const float *gamma, double *sums, float *dx,
                      float *dgamma_dbeta, void *stream);
 
 /* ---- Generator tail: BatchNorm2d -> LeakyReLU/ReLU -> Conv2d(C, K<=3, 3, 1, 1) -> Tanh, fused -------------- */

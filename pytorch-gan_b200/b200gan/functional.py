@@ -198,22 +198,27 @@ class NormFn(torch.autograd.Function):
         x = _as_cl(x)
         if stats is not None and stats.numel() == 0:
             stats = None
-        y, mean_rstd = ops.norm_forward(
+        y, mean_rstd, scale_shift = ops.norm_forward(
             x, None if gamma is None else gamma.detach(), None if beta is None else beta.detach(), running_mean,
-            running_var, nbt, spec.per_sample, spec.eps, spec.momentum, spec.act, spec.slope, stats, spec.rtf_out)
+            running_var, nbt, spec.per_sample, spec.eps, spec.momentum, spec.act, spec.slope, stats, spec.rtf_out,
+            return_scale_shift=True)
         ctx.spec = spec
-        ctx.save_for_backward(x, y if spec.act != ACT_NONE else None, mean_rstd, gamma)
+        # LeakyReLU / ReLU masks are recomputed from x in backward (sign of x * scale + shift): y need not be kept
+        c_ = x.shape[1]
+        mask_from_x = spec.act in (ACT_LRELU, ACT_RELU) and c_ % 4 == 0 and c_ // 4 <= 256 and 256 % (c_ // 4) == 0
+        need_y = spec.act != ACT_NONE and not mask_from_x
+        ctx.save_for_backward(x, y if need_y else None, mean_rstd, gamma, scale_shift if mask_from_x else None)
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        x, y, mean_rstd, gamma = ctx.saved_tensors
+        x, y, mean_rstd, gamma, scale_shift = ctx.saved_tensors
         spec = ctx.spec
         dy = _as_cl(dy)
         need_params = gamma is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         dx, dgb = ops.norm_backward(dy, x, y, mean_rstd, None if gamma is None else gamma.detach(), spec.per_sample,
-                                    spec.eps, spec.act, spec.slope, need_params, spec.rtf_dx)
+                                    spec.eps, spec.act, spec.slope, need_params, spec.rtf_dx, scale_shift)
         dgamma = dbeta = None
         if need_params:
             n, c = x.shape[0], x.shape[1]

@@ -218,7 +218,7 @@ def new_stats(x, per_sample):
 
 
 def norm_forward(x, gamma, beta, running_mean, running_var, nbt, per_sample, eps, momentum, act=ACT_NONE, slope=0.0,
-                 stats=None, round_tf32=False):
+                 stats=None, round_tf32=False, return_scale_shift=False):
     """Training-mode BatchNorm2d / InstanceNorm2d.  Returns (y, mean_rstd)."""
     lib = _lib.load()
     d = _norm_desc(x, per_sample, eps, momentum, act, slope, round_tf32)
@@ -235,6 +235,8 @@ def norm_forward(x, gamma, beta, running_mean, running_var, nbt, per_sample, eps
     y = torch.empty_like(x, memory_format=CL)
     _lib.check(lib.b200gan_norm_apply(ctypes.byref(d), x.data_ptr(), scale_shift.data_ptr(), y.data_ptr(), st),
                "norm_apply")
+    if return_scale_shift:
+        return y, mean_rstd, scale_shift
     return y, mean_rstd
 
 
@@ -306,7 +308,7 @@ def norm_apply_affine(x, scale_shift, per_sample, act=ACT_NONE, slope=0.0):
 
 
 def norm_backward(dy, x, y, mean_rstd, gamma, per_sample, eps, act=ACT_NONE, slope=0.0, need_params=False,
-                  round_tf32=False):
+                  round_tf32=False, scale_shift=None):
     lib = _lib.load()
     d = _norm_desc(x, per_sample, eps, 0.0, act, slope, round_tf32)
     groups = mean_rstd.numel() // 2
@@ -314,7 +316,8 @@ def norm_backward(dy, x, y, mean_rstd, gamma, per_sample, eps, act=ACT_NONE, slo
     dx = torch.empty_like(x, memory_format=CL)
     dgb = torch.empty(2 * groups, device=x.device, dtype=torch.float32) if need_params else None
     _lib.check(lib.b200gan_norm_bwd(ctypes.byref(d), dy.data_ptr(), x.data_ptr(), _ptr(y), mean_rstd.data_ptr(),
-                                    _ptr(gamma), sums.data_ptr(), dx.data_ptr(), _ptr(dgb), _stream()), "norm_bwd")
+                                    _ptr(scale_shift), _ptr(gamma), sums.data_ptr(), dx.data_ptr(), _ptr(dgb), _stream()),
+               "norm_bwd")
     return dx, dgb
 
 

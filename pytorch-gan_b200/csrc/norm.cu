@@ -216,6 +216,165 @@ __global__ void norm_bwd_params_kernel(double *__restrict__ sums, float *__restr
   sums[G + g] = 0.0;
 }
 
+
+// ---- fast paths (C % 4 == 0, 256 % (C/4) == 0): a thread keeps ONE float4 channel group for its whole loop, so there is
+// no index arithmetic beyond an add per element (the generic kernels above spend most of their time in 64-bit div/mod).
+// grid = (row blocks, samples): blockIdx.y selects the sample for per-sample (InstanceNorm) groups, else gridDim.y == 1.
+__global__ void __launch_bounds__(256)
+norm_apply_v4_kernel(const float *__restrict__ x, const float *__restrict__ scale_shift, float *__restrict__ y,
+                     int64_t rows, int C, int G, int act, float slope, int rtf) {
+  const int CV = C >> 2, cv = threadIdx.x % CV, rpb = 256 / CV;
+  const int gbase = (gridDim.y > 1 ? blockIdx.y * C : 0) + cv * 4;
+  const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale_shift + gbase));
+  const float4 sh = __ldg(reinterpret_cast<const float4 *>(scale_shift + G + gbase));
+  const int64_t base = (gridDim.y > 1 ? (int64_t)blockIdx.y * rows : 0);
+  const float4 *x4 = reinterpret_cast<const float4 *>(x) + base * CV + cv;
+  float4 *y4 = reinterpret_cast<float4 *>(y) + base * CV + cv;
+  const int64_t step = (int64_t)gridDim.x * rpb;
+#pragma unroll 4
+  for (int64_t r = (int64_t)blockIdx.x * rpb + threadIdx.x / CV; r < rows; r += step) {
+    const float4 v = __ldg(x4 + r * CV);
+    float4 o;
+    o.x = apply_act(fmaf(v.x, sc.x, sh.x), act, slope);
+    o.y = apply_act(fmaf(v.y, sc.y, sh.y), act, slope);
+    o.z = apply_act(fmaf(v.z, sc.z, sh.z), act, slope);
+    o.w = apply_act(fmaf(v.w, sc.w, sh.w), act, slope);
+    if (rtf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    y4[r * CV] = o;
+  }
+}
+
+// derivative of the fused activation: from the pre-activation value recomputed from x (scale_shift given: LeakyReLU /
+// ReLU masks need no saved output) or from the saved output y
+__device__ __forceinline__ float norm_act_grad(float xv, float sc, float sh, float yv, bool from_x, int act, float slope) {
+  if (act == B200GAN_ACT_NONE) return 1.f;
+  if (from_x) {
+    const float pre = fmaf(xv, sc, sh);
+    return act == B200GAN_ACT_LRELU ? (pre > 0.f ? 1.f : slope) : (pre > 0.f ? 1.f : 0.f);
+  }
+  return act_grad_from_out(yv, act, slope);
+}
+
+__global__ void __launch_bounds__(256)
+norm_bwd_reduce_v4_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ y,
+                          const float *__restrict__ mean_rstd, const float *__restrict__ scale_shift,
+                          double *__restrict__ sums, int64_t rows, int C, int G, int act, float slope) {
+  __shared__ float red[256][8];
+  const int CV = C >> 2, cv = threadIdx.x % CV, rpb = 256 / CV;
+  const int gbase = (gridDim.y > 1 ? blockIdx.y * C : 0) + cv * 4;
+  const bool from_x = scale_shift != nullptr && (act == B200GAN_ACT_LRELU || act == B200GAN_ACT_RELU);
+  float mean[4], rstd[4], sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mean[j] = __ldg(mean_rstd + gbase + j);
+    rstd[j] = __ldg(mean_rstd + G + gbase + j);
+    if (from_x) {
+      sc[j] = __ldg(scale_shift + gbase + j);
+      sh[j] = __ldg(scale_shift + G + gbase + j);
+    }
+  }
+  const int64_t base = (gridDim.y > 1 ? (int64_t)blockIdx.y * rows : 0);
+  const float4 *dy4 = reinterpret_cast<const float4 *>(dy) + base * CV + cv;
+  const float4 *x4 = reinterpret_cast<const float4 *>(x) + base * CV + cv;
+  const float4 *y4 = reinterpret_cast<const float4 *>(y) + base * CV + cv;
+  const bool need_y = act != B200GAN_ACT_NONE && !from_x;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t step = (int64_t)gridDim.x * rpb;
+#pragma unroll 4
+  for (int64_t r = (int64_t)blockIdx.x * rpb + threadIdx.x / CV; r < rows; r += step) {
+    const float4 d = __ldg(dy4 + r * CV), xv = __ldg(x4 + r * CV);
+    float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need_y) yv = __ldg(y4 + r * CV);
+    const float dd[4] = {d.x, d.y, d.z, d.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dz = dd[j] * norm_act_grad(xx[j], sc[j], sh[j], yy[j], from_x, act, slope);
+      a[j] += dz;
+      b[j] = fmaf(dz, (xx[j] - mean[j]) * rstd[j], b[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[threadIdx.x][j] = a[j];
+    red[threadIdx.x][4 + j] = b[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < CV) {
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < rpb; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] += (double)red[r * CV + threadIdx.x][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(sums + gbase + j, t[j]);
+      atomicAdd(sums + G + gbase + j, t[4 + j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+norm_bwd_apply_v4_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ y,
+                         const float *__restrict__ mean_rstd, const float *__restrict__ scale_shift,
+                         const float *__restrict__ gamma, const double *__restrict__ sums, float *__restrict__ dx,
+                         int64_t rows, int C, int G, float inv_count, int act, float slope, int rtf) {
+  const int CV = C >> 2, cv = threadIdx.x % CV, rpb = 256 / CV;
+  const int gbase = (gridDim.y > 1 ? blockIdx.y * C : 0) + cv * 4;
+  const bool from_x = scale_shift != nullptr && (act == B200GAN_ACT_LRELU || act == B200GAN_ACT_RELU);
+  float mean[4], rstd[4], gr[4], m1[4], m2[4], sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mean[j] = __ldg(mean_rstd + gbase + j);
+    rstd[j] = __ldg(mean_rstd + G + gbase + j);
+    gr[j] = (gamma ? __ldg(gamma + cv * 4 + j) : 1.f) * rstd[j];
+    m1[j] = (float)sums[gbase + j] * inv_count;
+    m2[j] = (float)sums[G + gbase + j] * inv_count;
+    if (from_x) {
+      sc[j] = __ldg(scale_shift + gbase + j);
+      sh[j] = __ldg(scale_shift + G + gbase + j);
+    }
+  }
+  const int64_t base = (gridDim.y > 1 ? (int64_t)blockIdx.y * rows : 0);
+  const float4 *dy4 = reinterpret_cast<const float4 *>(dy) + base * CV + cv;
+  const float4 *x4 = reinterpret_cast<const float4 *>(x) + base * CV + cv;
+  const float4 *y4 = reinterpret_cast<const float4 *>(y) + base * CV + cv;
+  float4 *dx4 = reinterpret_cast<float4 *>(dx) + base * CV + cv;
+  const bool need_y = act != B200GAN_ACT_NONE && !from_x;
+  const int64_t step = (int64_t)gridDim.x * rpb;
+#pragma unroll 4
+  for (int64_t r = (int64_t)blockIdx.x * rpb + threadIdx.x / CV; r < rows; r += step) {
+    const float4 d = __ldg(dy4 + r * CV), xv = __ldg(x4 + r * CV);
+    float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need_y) yv = __ldg(y4 + r * CV);
+    const float dd[4] = {d.x, d.y, d.z, d.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dz = dd[j] * norm_act_grad(xx[j], sc[j], sh[j], yy[j], from_x, act, slope);
+      const float v = gr[j] * (dz - m1[j] - ((xx[j] - mean[j]) * rstd[j]) * m2[j]);
+      o[j] = rtf ? round_tf32(v) : v;
+    }
+    dx4[r * CV] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static bool fast_path(const b200gan_norm_desc *d, const void *a, const void *b, const void *c, const void *e) {
+  if (d->C % 4 != 0) return false;
+  const int CV = d->C / 4;
+  if (CV > 256 || 256 % CV != 0) return false;
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)e) & 15) == 0;
+}
+// (row blocks, samples) with ~8 blocks per SM in total
+static dim3 fast_grid(const b200gan_norm_desc *d, int64_t &rows) {
+  rows = d->per_sample ? (int64_t)d->HW : (int64_t)d->N * d->HW;
+  const int ny = d->per_sample ? d->N : 1;
+  const int rpb = 256 / (d->C / 4);
+  int64_t want = (148 * 8 + ny - 1) / ny;
+  int64_t maxb = ceil_div64(rows, (int64_t)rpb * 4);
+  if (want > maxb) want = maxb;
+  if (want < 1) want = 1;
+  return dim3((unsigned)want, (unsigned)ny, 1);
+}
+
 static void reduce_grid(const b200gan_norm_desc *d, dim3 &grid, int64_t &rows, int64_t &rpb) {
   rows = d->per_sample ? (int64_t)d->HW : (int64_t)d->N * d->HW;
   int xb = ceil_div(d->C, 32);
@@ -277,6 +436,14 @@ extern "C" int b200gan_norm_apply(const b200gan_norm_desc *d, const float *x,
   B2_CHECK_ARG(x && scale_shift && y, "norm_apply: null pointer");
   int G = d->per_sample ? d->N * d->C : d->C;
   int64_t total = (int64_t)d->N * d->HW * d->C;
+  if (fast_path(d, x, y, scale_shift, x) && G % 4 == 0) {
+    int64_t rows;
+    dim3 grid = fast_grid(d, rows);
+    norm_apply_v4_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, scale_shift, y, rows, d->C, G, d->act, d->slope,
+                                                              d->round_tf32);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   bool vec = (d->C % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) % 16 == 0);
   int64_t tv = vec ? total / 4 : total;
   int64_t blocks = ceil_div64(tv, 256);
@@ -292,16 +459,34 @@ extern "C" int b200gan_norm_apply(const b200gan_norm_desc *d, const float *x,
 }
 
 extern "C" int b200gan_norm_bwd(const b200gan_norm_desc *d, const float *dy, const float *x,
-                                const float *y, const float *mean_rstd, const float *gamma,
-                                double *sums, float *dx, float *dgamma_dbeta, void *stream) {
+                                const float *y, const float *mean_rstd, const float *scale_shift,
+                                const float *gamma, double *sums, float *dx, float *dgamma_dbeta, void *stream) {
   if (int e = check_desc(d)) return e;
   B2_CHECK_ARG(dy && x && mean_rstd && sums && dx, "norm_bwd: null pointer");
-  B2_CHECK_ARG(d->act == B200GAN_ACT_NONE || y != nullptr, "norm_bwd: fused activation needs y");
+  const bool from_x = scale_shift && (d->act == B200GAN_ACT_LRELU || d->act == B200GAN_ACT_RELU);
+  B2_CHECK_ARG(d->act == B200GAN_ACT_NONE || from_x || y != nullptr,
+               "norm_bwd: fused activation needs the saved output y (or scale_shift for LeakyReLU / ReLU)");
   cudaStream_t st = as_stream(stream);
+  int G = d->per_sample ? d->N * d->C : d->C;
+  if (fast_path(d, dy, x, dx, y ? (const void *)y : (const void *)x) && G % 4 == 0 &&
+      (((uintptr_t)mean_rstd | (uintptr_t)(scale_shift ? scale_shift : mean_rstd)) & 3) == 0) {
+    int64_t rows2;
+    dim3 g2 = fast_grid(d, rows2);
+    const float *yy = y ? y : x;  // never dereferenced when the mask comes from x
+    norm_bwd_reduce_v4_kernel<<<g2, 256, 0, st>>>(dy, x, yy, mean_rstd, scale_shift, sums, rows2, d->C, G, d->act, d->slope);
+    B2_LAUNCH_CHECK();
+    float inv = (float)(1.0 / (d->per_sample ? (double)d->HW : (double)d->N * (double)d->HW));
+    norm_bwd_apply_v4_kernel<<<g2, 256, 0, st>>>(dy, x, yy, mean_rstd, scale_shift, gamma, sums, dx, rows2, d->C, G, inv,
+                                                 d->act, d->slope, d->round_tf32);
+    B2_LAUNCH_CHECK();
+    norm_bwd_params_kernel<<<ceil_div(G, 128), 128, 0, st>>>(sums, dgamma_dbeta, G);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
+  B2_CHECK_ARG(d->act == B200GAN_ACT_NONE || y != nullptr, "norm_bwd: this geometry needs the saved output y");
   dim3 grid;
   int64_t rows, rpb;
   reduce_grid(d, grid, rows, rpb);
-  int G = d->per_sample ? d->N * d->C : d->C;
   norm_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, x, y, mean_rstd, sums, d->C, rows, rpb, G,
                                                        d->per_sample, d->act, d->slope);
   B2_LAUNCH_CHECK();
