@@ -349,7 +349,8 @@ def build_job(torch, config, stock, dev, world, rank):
         rd = reducer(d.parameters(), od)
 
         def step(imgs, z, alpha):
-            dl, gp = train.wgan_gp_critic_step(g, d, od, imgs, z, alpha, 10.0, fused_gp=not stock, reduce_d=rd)
+            dl, gp = train.wgan_gp_critic_step(g, d, od, imgs, z, alpha, 10.0, fused_gp=False if stock else "step",
+                                                 reduce_d=rd)
             return torch.stack([dl, gp])
         pools = [images(1), [torch.randn(B, LATENT, generator=gen).pin_memory() for _ in range(pool_n)],
                  [torch.rand(B, 1, 1, 1, generator=gen).pin_memory() for _ in range(pool_n)]]

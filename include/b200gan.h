@@ -264,6 +264,17 @@ int b200gan_gp_mlp_fwd_bwd(const b200gan_gp_mlp_desc *d, const float *xi, const 
                            float *gp, float *dW1, float *dW2, float *dW3, float *workspace,
                            void *stream);
 
+/* The whole critic iteration of wgan_gp.py:164-173 for the MLP critic in ONE cooperative kernel:
+ *   losses[0] = -mean(D(real)) + mean(D(fake)) + lambda * gp,   losses[1] = lambda * gp,
+ * with the interpolates alpha * real + (1 - alpha) * fake formed inside (alpha [N], wgan_gp.py:122-124), and the
+ * gradient of losses[0] w.r.t. every parameter of D (all OVERWRITTEN): first-order backward of the real / fake passes and
+ * the closed-form double backward of the penalty share their GEMMs (csrc/gp_mlp.cu).  real, fake: [N][Din]. */
+size_t b200gan_critic_step_workspace_floats(const b200gan_gp_mlp_desc *d);
+int b200gan_critic_step_mlp(const b200gan_gp_mlp_desc *d, const float *real, const float *fake, const float *alpha,
+                            const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                            const float *b3, float *losses, float *dW1, float *db1, float *dW2, float *db2, float *dW3,
+                            float *db3, float *workspace, void *stream);
+
 /* ---- flat-buffer Adam (torch.optim.Adam semantics: dcgan.py:134-135) --------------------- */
 /* p -= lr * mhat / (sqrt(vhat) + eps), bias-corrected with the step count read from the
  * device (step[0] is incremented by the kernel -> CUDA-graph capturable).  lr, betas and eps

@@ -93,6 +93,8 @@ SIGNATURES = {
     "b200gan_act_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_f32, c_i64, c_i32, c_i64, c_vp, c_vp]),
     "b200gan_gp_mlp_workspace_floats": (c_sz, [_P(GpMlpDesc)]),
     "b200gan_gp_mlp_fwd_bwd": (c_i32, [_P(GpMlpDesc)] + [c_vp] * 12),
+    "b200gan_critic_step_workspace_floats": (c_sz, [_P(GpMlpDesc)]),
+    "b200gan_critic_step_mlp": (c_i32, [_P(GpMlpDesc)] + [c_vp] * 18),
     "b200gan_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f32, c_vp, c_vp]),
     "b200gan_nb_supported": (c_i32, [_P(ConvGeom)]),
     "b200gan_nb_fprop": (c_i32, [_P(ConvGeom), _P(NbBn), c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_i32, c_f32, c_vp,

@@ -544,3 +544,34 @@ def gradient_penalty_mlp(critic_layers, xi, lambda_gp):
     l1, l2, l3 = mods[0], mods[2], mods[4]
     return GradientPenaltyMLPFn.apply(xi, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, float(mods[1].negative_slope),
                                       float(lambda_gp))
+
+
+class CriticStepMLPFn(torch.autograd.Function):
+    """d_loss = -mean(D(real)) + mean(D(fake)) + lambda * gp(D, interpolates) of wgan_gp.py:164-171 for the MLP critic,
+    with every parameter gradient produced by the same kernel (first-order backward + closed-form double backward)."""
+
+    @staticmethod
+    def forward(ctx, real, fake, alpha, w1, b1, w2, b2, w3, b3, slope, lambda_gp):
+        out = ops.critic_step_mlp(real.detach(), fake.detach(), alpha, *[t.detach().contiguous() for t in
+                                                                        (w1, b1, w2, b2, w3, b3)], slope, lambda_gp)
+        losses, grads = out[0], out[1:]
+        ctx.save_for_backward(*grads)
+        ctx.mark_non_differentiable(losses[1:])
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g, _g_gp):
+        return (None, None, None) + tuple(g * t for t in ctx.saved_tensors) + (None, None)
+
+
+def critic_step_mlp(critic_layers, real, fake, alpha, lambda_gp):
+    """critic_layers: nn.Sequential(Linear, LeakyReLU, Linear, LeakyReLU, Linear(-> 1)) (wgan_gp.py:72-78).
+    Returns (d_loss, lambda * gradient penalty); d_loss.backward() fills the gradients of all six parameters."""
+    mods = list(critic_layers)
+    if not (len(mods) == 5 and all(isinstance(mods[i], torch.nn.Linear) for i in (0, 2, 4)) and
+            all(isinstance(mods[i], torch.nn.LeakyReLU) for i in (1, 3)) and mods[4].out_features == 1 and
+            mods[1].negative_slope == mods[3].negative_slope and all(mods[i].bias is not None for i in (0, 2, 4))):
+        raise NotImplementedError("b200gan: fused critic step expects Linear-LReLU-Linear-LReLU-Linear(->1) with biases")
+    l1, l2, l3 = mods[0], mods[2], mods[4]
+    return CriticStepMLPFn.apply(real, fake, alpha, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias,
+                                 float(mods[1].negative_slope), float(lambda_gp))

@@ -502,3 +502,28 @@ def gp_mlp_fwd_bwd(xi, w1, b1, w2, b2, w3, slope, lambda_gp):
                                           b2.data_ptr(), w3.data_ptr(), gp.data_ptr(), dw1.data_ptr(), dw2.data_ptr(),
                                           dw3.data_ptr(), ws.data_ptr(), _stream()), "gp_mlp_fwd_bwd")
     return gp, dw1, dw2, dw3
+
+
+def critic_step_mlp(real, fake, alpha, w1, b1, w2, b2, w3, b3, slope, lambda_gp):
+    """wgan_gp.py:164-173 for the MLP critic in one kernel.  Returns (losses[2], dW1, db1, dW2, db2, dW3, db3)."""
+    for t_ in (real, fake, alpha, w1, b1, w2, b2, w3, b3):
+        _require_cuda(t_, "critic_step operand")
+    lib = _lib.load()
+    n = real.shape[0]
+    real, fake = real.contiguous().view(n, -1), fake.contiguous().view(n, -1)
+    alpha = alpha.contiguous().view(-1)
+    d = GpMlpDesc()
+    d.N, d.Din, d.H1, d.H2 = n, real.shape[1], w1.shape[0], w2.shape[0]
+    d.slope, d.lambda_gp = slope, lambda_gp
+    if (fake.shape != real.shape or alpha.numel() != n or w1.shape[1] != d.Din or w2.shape[1] != d.H1
+            or w3.numel() != d.H2):
+        raise RuntimeError("b200gan critic_step_mlp: shapes do not chain")
+    dev = real.device
+    ws = torch.empty(lib.b200gan_critic_step_workspace_floats(ctypes.byref(d)), device=dev, dtype=torch.float32)
+    losses = torch.empty(2, device=dev, dtype=torch.float32)
+    grads = [torch.empty_like(t_) for t_ in (w1, b1, w2, b2, w3, b3)]
+    _lib.check(lib.b200gan_critic_step_mlp(ctypes.byref(d), real.data_ptr(), fake.data_ptr(), alpha.data_ptr(),
+                                           w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(),
+                                           b3.data_ptr(), losses.data_ptr(), *[g.data_ptr() for g in grads],
+                                           ws.data_ptr(), _stream()), "critic_step_mlp")
+    return (losses, *grads)

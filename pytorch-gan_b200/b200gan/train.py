@@ -75,6 +75,13 @@ def wgan_gp_critic_step(generator, discriminator, opt_d, real_imgs, z, alpha, la
     opt_d.zero_grad()                                                     # :155
     with torch.no_grad():
         fake_imgs = generator(z)                                          # :161
+    if fused_gp == "step":
+        # the whole of :164-173 (three critic passes, penalty, backward) in one cooperative kernel
+        d_loss, gp_term = F.critic_step_mlp(discriminator.model, real_imgs, fake_imgs, alpha, lambda_gp)
+        d_loss.backward()
+        _opt_step(opt_d, reduce_d)
+        _join(reduce_d)
+        return d_loss.detach(), gp_term.detach()
     real_validity = discriminator(real_imgs)                              # :164
     fake_validity = discriminator(fake_imgs)                              # :166
     interpolates = alpha * real_imgs + (1 - alpha) * fake_imgs            # :124

@@ -79,3 +79,48 @@ def test_wgan_gp_critic_and_generator_steps():
     assert abs(gl.item() - gl_r.item()) < TOL * max(abs(gl_r.item()), 1.0)
     for (k, po), (_, pr) in zip(d.named_parameters(), d_ref.named_parameters()):
         assert rel_err(po, pr) < TOL, k
+
+
+@pytest.mark.parametrize("batch,img", [(64, 32), (5, 28)])
+def test_whole_critic_iteration_in_one_kernel(batch, img):
+    """b200gan_critic_step_mlp: -mean(D(real)) + mean(D(fake)) + lambda * gp and all six parameter gradients against
+    autograd on stock torch (the oracle's compute_gradient_penalty, wgan_gp.py:119-138,164-173)."""
+    from b200gan import functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _, d_ref, _, d = _build(img, seed=4)
+    torch.manual_seed(12)
+    real = torch.randn(batch, 1, img, img, device="cuda")
+    fake = torch.randn(batch, 1, img, img, device="cuda")
+    alpha = torch.rand(batch, 1, 1, 1, device="cuda")
+    gp_ref = ref_models.compute_gradient_penalty(d_ref, real, fake, alpha)
+    loss_ref = -torch.mean(d_ref(real)) + torch.mean(d_ref(fake)) + 10.0 * gp_ref
+    loss_ref.backward()
+    loss, gp = F.critic_step_mlp(d.model, real, fake, alpha, 10.0)
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * max(abs(loss_ref.item()), 1.0)
+    assert abs(gp.item() - 10.0 * gp_ref.item()) < 1e-4 * abs(10.0 * gp_ref.item())
+    for (k, po), (_, pr) in zip(d.named_parameters(), d_ref.named_parameters()):
+        den = pr.grad.double().norm().item()
+        if den < 1e-9:     # the last bias: -1 + 1 = 0 exactly
+            assert po.grad.abs().max().item() < 1e-6, k
+        else:
+            assert rel_err(po.grad, pr.grad) < TOL, k
+
+
+def test_wgan_gp_critic_steps_with_the_one_kernel_iteration():
+    from b200gan import optim, train
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g_ref, d_ref, g, d = _build(32, seed=1)
+    od_r = torch.optim.Adam(d_ref.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    od = optim.Adam(d.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    n = 64
+    for it in range(4):
+        real = ref_models.synthetic_images(n, 1, 32, 32, seed=30 + it).cuda()
+        z = ref_models.synthetic_z(n, seed=30 + it).cuda()
+        alpha = ref_models.synthetic_alpha(n, seed=30 + it).cuda()
+        dl_r, gp_r = train.wgan_gp_critic_step(g_ref, d_ref, od_r, real, z, alpha, 10.0, fused_gp=False)
+        dl, gp = train.wgan_gp_critic_step(g, d, od, real, z, alpha, 10.0, fused_gp="step")
+        assert abs(dl.item() - dl_r.item()) < TOL * max(abs(dl_r.item()), 1.0), it
+        assert abs(gp.item() - gp_r.item()) < TOL * abs(gp_r.item()), it
+    for (k, po), (_, pr) in zip(d.named_parameters(), d_ref.named_parameters()):
+        assert rel_err(po, pr) < TOL, k
