@@ -242,82 +242,93 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     if (threadIdx.x == 64) TC_TRACE(40);
+    // The staging tile is written 128 output channels (four 16 KB chunks) at a time: BN = 256 takes two rounds through
+    // the same four buffers, the second one after the first round's TMA stores have finished reading shared memory.
+    constexpr int ROUND = BN < 128 ? BN : 128;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      if (threadIdx.x == 64) TC_TRACE(48 + (c >> 5) * 3);
-      tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (threadIdx.x == 64) TC_TRACE(49 + (c >> 5) * 3);
-      // every option is tested ONCE per chunk, never per element: a switch inside the unrolled element loop
-      // becomes 32 indirect branches into a 50 KB body and costs ~200 cycles each (measured: 6.5k cycles/chunk)
-      if (p.bias) {
-        const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + ntile * BN + c);
+    for (int c0 = 0; c0 < BN; c0 += ROUND) {
+      if (c0 > 0) {
+        if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+#pragma unroll 1
+      for (int c = c0; c < c0 + ROUND; c += 32) {
+        float v[32];
+        if (threadIdx.x == 64) TC_TRACE(48 + ((c >> 5) & 3) * 3);
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        if (threadIdx.x == 64) TC_TRACE(49 + ((c >> 5) & 3) * 3);
+        // every option is tested ONCE per chunk, never per element: a switch inside the unrolled element loop
+        // becomes 32 indirect branches into a 50 KB body and costs ~200 cycles each (measured: 6.5k cycles/chunk)
+        if (p.bias) {
+          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + ntile * BN + c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 b = __ldg(b4 + j);
-          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (act == B200GAN_ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+        } else if (act == B200GAN_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (act == B200GAN_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        } else if (act == B200GAN_ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        }
+        if (cs && valid) {
+          const float4 *s4 = reinterpret_cast<const float4 *>(cs + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(s4 + j);
+            v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w;
+          }
+        }
+        if (rtf) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        }
+        {
+          uint8_t *row = smem + (((c - c0) >> 5)) * TC_A_BYTES + m * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4 *>(row + ((j ^ (m & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (threadIdx.x == 64) TC_TRACE(50 + ((c >> 5) & 3) * 3);
+        if (p.stats) {
+          float s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = valid ? v[j] : 0.f;
+            s2[j] = v[j] * v[j];
+          }
+          float cs1 = warp_colsum32(v, lane);
+          float cs2 = warp_colsum32(s2, lane);
+          red[(q * BN + c + lane) * 2 + 0] = cs1;
+          red[(q * BN + c + lane) * 2 + 1] = cs2;
         }
       }
-      if (act == B200GAN_ACT_LRELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
-      } else if (act == B200GAN_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (act == B200GAN_ACT_TANH) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-      } else if (act == B200GAN_ACT_SIGMOID) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
-      }
-      if (cs && valid) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(cs + c);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 b = __ldg(s4 + j);
-          v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w;
-        }
-      }
-      if (rtf) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-      }
-      {
-        uint8_t *row = smem + (c >> 5) * TC_A_BYTES + m * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4 *>(row + ((j ^ (m & 7)) << 4)) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      if (threadIdx.x == 64) TC_TRACE(50 + (c >> 5) * 3);
-      if (p.stats) {
-        float s2[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = valid ? v[j] : 0.f;
-          s2[j] = v[j] * v[j];
-        }
-        float cs1 = warp_colsum32(v, lane);
-        float cs2 = warp_colsum32(s2, lane);
-        red[(q * BN + c + lane) * 2 + 0] = cs1;
-        red[(q * BN + c + lane) * 2 + 1] = cs2;
+      if (threadIdx.x == 64) TC_TRACE(43);
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the async (TMA) proxy
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        TC_TRACE(44);
+#pragma unroll 1
+        for (int c = c0; c < c0 + ROUND; c += 32)
+          tma_store_5d(&tmY, smem + ((c - c0) >> 5) * TC_A_BYTES, p.out_dc[ph] + ntile * BN + c, w0, p.out_da[ph], h0, n0);
+        TC_TRACE(45);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (threadIdx.x == 64) TC_TRACE(43);
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the async (TMA) proxy
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 64) {
-      TC_TRACE(44);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32)
-        tma_store_5d(&tmY, smem + (c >> 5) * TC_A_BYTES, p.out_dc[ph] + ntile * BN + c, w0, p.out_da[ph], h0, n0);
-      TC_TRACE(45);
-      tma_store_commit_and_wait_read();
-    }
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (p.stats) {
-      const int e = threadIdx.x - 64;
-      if (e < BN) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // every warp's partial sums are in `red`
+      for (int e = threadIdx.x - 64; e < BN; e += 128) {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
@@ -679,7 +690,7 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
                   int btaps, int nphase, const int *tap_begin, const TcTap *taps, int Ho, int Wo, bool phase_out,
                   const int *out_dc, const int *out_da, int ldk, const b200gan_epilogue *ep, float *y,
                   cudaStream_t st) {
-  const int BN = (Kout % 128 == 0) ? 128 : (Kout % 64 == 0 ? 64 : 32);
+  int BN = (Kout % 128 == 0) ? 128 : (Kout % 64 == 0 ? 64 : 32);
   TcParams p;
   memset(&p, 0, sizeof(p));
   const int total_taps = tap_begin[nphase];
@@ -696,6 +707,13 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   p.bh_log2 = bhl;
   p.tiles_w = ceil_div(Wo, BW);
   p.tiles_h = ceil_div(Ho, BH);
+  {
+    // 256-wide tiles (A 16 KB + B 32 KB per stage feed 4 x M128 N256 K8: operand ingest and tensor time balance) when
+    // the layer still gives every SM a CTA
+    static const bool bn256 = !(getenv("B200GAN_TC_BN256") && atoi(getenv("B200GAN_TC_BN256")) == 0);
+    const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * ceil_div(N, BNn) * nphase;
+    if (bn256 && Kout % 256 == 0 && tiles * (Kout / 256) >= 148) BN = 256;
+  }
   p.N = N;
   p.Ho = Ho;
   p.Wo = Wo;
@@ -762,6 +780,7 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
     if (int e = make_tmap_f32(&tmB, packedB, 2, dims, strides, box)) return e;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)nphase);
+  if (BN == 256) return launch_tc<256, 2>(tmA, tmB, tmY, p, grid, st);
   if (BN == 128) return launch_tc<128, 3>(tmA, tmB, tmY, p, grid, st);
   if (BN == 64) return launch_tc<64, 4>(tmA, tmB, tmY, p, grid, st);
   return launch_tc<32, 4>(tmA, tmB, tmY, p, grid, st);

@@ -21,8 +21,7 @@
 
 namespace b200gan {
 
-constexpr int WG_PIX = 32;            // pixels (GEMM-K) per pipeline stage
-constexpr int WG_CHUNK_BYTES = WG_PIX * 128;  // one 32-channel chunk of one stage
+// pixels (GEMM-K) per pipeline stage: 32 (4 KB boxes) or 64 (8 KB boxes: half as many TMA instructions per byte)
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_JOBS = 52;
 
@@ -49,10 +48,11 @@ struct WgParams {
   uint32_t lbo, sbo;              // UMMA descriptor byte offsets (chunk stride, 8-row group stride)
 };
 
-template <int NB, int STAGES>
+template <int NB, int STAGES, int WG_PIX>
 __global__ void __launch_bounds__(WG_THREADS, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                 const __grid_constant__ CUtensorMap tmP, const __grid_constant__ WgParams p) {
+  constexpr int WG_CHUNK_BYTES = WG_PIX * 128;           // one 32-channel chunk of one stage
   constexpr int A_BYTES = 4 * WG_CHUNK_BYTES;            // 128 channels
   constexpr int B_BYTES = (NB / 32) * WG_CHUNK_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -103,7 +103,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int tw = t % p.tiles_w;
         t /= p.tiles_w;
         const int th = t % p.tiles_h;
-        const int n = (t / p.tiles_h) * p.imgs_per_box;  // a 32-pixel box spans several images when H*W < 32
+        const int n = (t / p.tiles_h) * p.imgs_per_box;  // a box spans several images when H*W < WG_PIX
         const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t *sa = smem + stage * STAGE_BYTES;
@@ -242,7 +242,17 @@ struct WgPlan {
   int s_is_a, NB, mtiles, ntiles, mtotal, ldn, njobs, bwl, bhl, tiles_w, tiles_h, tiles_total, nsplits, tps, Ho, Wo;
   int sch, dch;  // channels of the shifted / dense operand
   int ipb;
+  int pix;       // pixels per stage (32 or 64)
 };
+
+static int wg_pix_pref() {
+  static const int v = [] {
+    const char *e = getenv("B200GAN_WG_PIX");
+    const int x = e ? atoi(e) : 64;
+    return x == 32 ? 32 : 64;
+  }();
+  return v;
+}
 
 static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
   if (g->pad_mode != B200GAN_PAD_ZERO || g->N < 1) return false;
@@ -274,13 +284,16 @@ static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
   // pixel grid the contraction runs over = grid of the dense operand (low-res grid for the upsample fold)
   pl.Ho = up2 ? g->H : (g->transposed ? g->H : g->P);
   pl.Wo = up2 ? g->W : (g->transposed ? g->W : g->Q);
+  // 64-pixel stages for the 64-wide B operand (two CTAs per SM still fit with two stages); 128-wide keeps 32
+  pl.pix = (pl.NB == 64 && wg_pix_pref() == 64 && (int64_t)pl.Ho * pl.Wo >= 64) ? 64 : 32;
+  const int pl2 = pl.pix == 64 ? 6 : 5;
   pl.bwl = ilog2c(pl.Wo);
-  if (pl.bwl > 5) pl.bwl = 5;
+  if (pl.bwl > pl2) pl.bwl = pl2;
   pl.bhl = ilog2c(pl.Ho);
-  if (pl.bhl > 5 - pl.bwl) pl.bhl = 5 - pl.bwl;
+  if (pl.bhl > pl2 - pl.bwl) pl.bhl = pl2 - pl.bwl;
   pl.tiles_w = ceil_div(pl.Wo, 1 << pl.bwl);
   pl.tiles_h = ceil_div(pl.Ho, 1 << pl.bhl);
-  pl.ipb = 32 >> (pl.bwl + pl.bhl);  // images per 32-pixel box (>1 only when the whole map has < 32 pixels)
+  pl.ipb = pl.pix >> (pl.bwl + pl.bhl);  // images per box (>1 only when the whole map has fewer pixels than a stage)
   int64_t tt = (int64_t)ceil_div(g->N, pl.ipb) * pl.tiles_w * pl.tiles_h;
   if (tt > (1 << 30)) return false;
   pl.tiles_total = (int)tt;
@@ -306,13 +319,13 @@ size_t tc_wgrad_workspace_floats(const b200gan_conv_geom *g) {
   return (size_t)pl.njobs * pl.mtotal * pl.ldn;
 }
 
-template <int NB, int STAGES>
+template <int NB, int STAGES, int PIX>
 static int launch_wg(const CUtensorMap &tmX, const CUtensorMap &tmY, const CUtensorMap &tmP, const WgParams &p, dim3 grid,
                      cudaStream_t st) {
-  constexpr int SMEM = STAGES * (4 + NB / 32) * WG_CHUNK_BYTES + 1024 + 256;
+  constexpr int SMEM = STAGES * (4 + NB / 32) * (PIX * 128) + 1024 + 256;
   static std::atomic<uint64_t> attr_done{0};
-  if (int e = ensure_dynamic_smem(wgrad_tc_kernel<NB, STAGES>, SMEM, attr_done)) return e;
-  wgrad_tc_kernel<NB, STAGES><<<grid, WG_THREADS, SMEM, st>>>(tmX, tmY, tmP, p);
+  if (int e = ensure_dynamic_smem(wgrad_tc_kernel<NB, STAGES, PIX>, SMEM, attr_done)) return e;
+  wgrad_tc_kernel<NB, STAGES, PIX><<<grid, WG_THREADS, SMEM, st>>>(tmX, tmY, tmP, p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
@@ -354,7 +367,7 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   p.tiles_total = pl.tiles_total; p.tiles_per_split = pl.tps;
   p.s_is_a = pl.s_is_a; p.mtiles = pl.mtiles; p.ntiles = pl.ntiles; p.ldn = pl.ldn; p.mtotal = pl.mtotal;
   p.partial = ws;
-  p.lbo = WG_CHUNK_BYTES;
+  p.lbo = pl.pix * 128;
   p.sbo = 512;
 
   // operand tensors: Conv2d: S = x [N][H][W][C], D = dy [N][P][Q][K]; ConvTranspose2d: S = dy, D = x
@@ -394,8 +407,10 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   }
   B2_CUDA(cudaMemsetAsync(ws, 0, (size_t)pl.njobs * pl.mtotal * pl.ldn * sizeof(float), st));
   dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
-  int rc = pl.NB == 128 ? launch_wg<128, 3>(tmX, tmY, tmP, p, grid, st)
-                        : (pl.NB == 64 ? launch_wg<64, 4>(tmX, tmY, tmP, p, grid, st) : launch_wg<32, 4>(tmX, tmY, tmP, p, grid, st));
+  int rc = pl.NB == 128 ? launch_wg<128, 3, 32>(tmX, tmY, tmP, p, grid, st)
+           : pl.NB == 64 ? (pl.pix == 64 ? launch_wg<64, 2, 64>(tmX, tmY, tmP, p, grid, st)
+                                         : launch_wg<64, 4, 32>(tmX, tmY, tmP, p, grid, st))
+                         : launch_wg<32, 4, 32>(tmX, tmY, tmP, p, grid, st);
   if (rc) return rc;
   WgReduceP rp;
   rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.njobs = pl.njobs;

@@ -49,6 +49,8 @@ CONV_CASES = [  # cin, cout, k, stride, pad, H, W, N   -- every geometry of SURV
     (128, 64, 3, 1, 1, 24, 20, 3),   # tensor-core with ragged tiles
     (256, 256, 3, 1, 0, 18, 18, 1),  # cyclegan residual conv on a padded map
     (64, 128, 7, 1, 3, 16, 16, 1),
+    (64, 256, 3, 1, 1, 64, 48, 7),   # 256-wide tcgen05 tiles in fprop (>= 148 tiles), ragged
+    (256, 32, 3, 2, 1, 64, 64, 8),   # ... and in the (scatter-form, four-phase) data gradient
 ]
 
 
