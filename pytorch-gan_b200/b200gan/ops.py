@@ -58,6 +58,13 @@ def to_cl(x):
     _require_cuda(x, "input")
     if is_cl(x):
         return x
+    if x.dim() == 4 and x.stride(1) == 1 and not x.is_contiguous():
+        # channel-innermost but not dense: a channel slice of a channels_last tensor (the gradient of one input of
+        # torch.cat(..., 1), pix2pix/models.py:50,132).  One strided copy, coalesced along C -- not a round trip
+        # through NCHW.
+        y = empty_cl(*x.shape, x.device)
+        y.copy_(x)
+        return y
     if not x.is_contiguous():
         x = x.contiguous()
     n, c, h, w = x.shape

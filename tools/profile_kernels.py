@@ -46,8 +46,16 @@ def main():
         ("D conv2 16->32 s2 @32", 16, 32, 3, 2, 1, 32, 32, 1),
         ("D conv3 32->64 s2 @16", 32, 64, 3, 2, 1, 16, 16, 1),
         ("D conv4 64->128 s2 @8", 64, 128, 3, 2, 1, 8, 8, 1),
+        # CycleGAN / Pix2Pix interior layers (batch 8 / 16)
+        ("CG res 256->256 @64 (bs8)", 256, 256, 3, 1, 1, 64, 64, 1, 8),
+        ("CG down 128->256 s2 @128 (bs8)", 128, 256, 3, 2, 1, 128, 128, 1, 8),
+        ("CG up2 256->128 @64 (bs8)", 256, 128, 3, 1, 1, 64, 64, 2, 8),
+        ("P2P down 128->256 k4s2 @64 (bs16)", 128, 256, 4, 2, 1, 64, 64, 1, 16),
+        ("P2P down 256->512 k4s2 @32 (bs16)", 256, 512, 4, 2, 1, 32, 32, 1, 16),
     ]
-    for name, cin, cout, k, s, p, h, w, up in layers:
+    for entry in layers:
+        name, cin, cout, k, s, p, h, w, up = entry[:9]
+        n = entry[9] if len(entry) > 9 else 128
         x = torch.randn(n, cin, h, w, device="cuda").contiguous(memory_format=CL)
         wt = torch.randn(cout, cin, k, k, device="cuda") * 0.02
         g, oshape = ops.make_geom(tuple(x.shape), tuple(wt.shape), s, (p, p, p, p), 0, up, False)
@@ -76,6 +84,7 @@ def main():
     for r in rows:
         print(f"{r[0]:28s} {r[1]:6s} {r[2]:8s} {r[3]:9.1f} {r[4]:9.2f} {r[5]:10.0f}")
     # normalisation / element-wise passes on the largest tensor of the step ([128,64,64,64] = 134 MB)
+    n = 128
     x = torch.randn(n, 64, 64, 64, device="cuda").contiguous(memory_format=CL)
     gamma = torch.ones(64, device="cuda")
     beta = torch.zeros(64, device="cuda")
