@@ -249,7 +249,13 @@ class Linear(_T["Linear"]):
     """nn.Linear.  Inside a Sequential, Linear(K, 1) + Sigmoid -- the head of a discriminator (dcgan.py:92) -- runs as
     one b200gan kernel per direction (Sequential._forward_2d); on its own it is a plain library GEMM and stays on
     torch/cuBLAS (wgan_gp.py:46-60,72-78; dcgan.py:50), which also keeps the critic of wgan_gp.py double-differentiable
-    for the script's own autograd.grad(create_graph=True)."""
+    for the script's own autograd.grad(create_graph=True).  A wide output (>= 8192 features: the generator's first
+    layer, dcgan.py:50) uses the TF32 library GEMM like the convolutions behind it."""
+
+    def forward(self, x):
+        if _gpu2d_f32(x) and self.out_features >= 8192 and ops.Config.algo != "simt":
+            return F.LinearWideFn.apply(x, self.weight, self.bias)
+        return super().forward(x)
 
 
 class BCELoss(_T["BCELoss"]):

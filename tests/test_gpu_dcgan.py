@@ -189,3 +189,20 @@ def test_dcgan_training_steps_with_dropout_and_adam():
             assert rel_err(po - p0, pr - p0) < step_tol, k
         else:
             assert rel_err(po, pr) < 2 * TOL, k
+
+
+def test_a_script_in_the_reference_idiom_runs_under_the_launcher_on_the_gpu():
+    """launch.run() of a stand-alone script written in the reference's API idiom (tests/scripts/mini_convgan): torch.nn
+    looked up by attribute, Sequential(*layers), .apply init by class name, torch.cuda.FloatTensor(numpy), Variable,
+    torch.optim.Adam -- stock torch vs the b200gan drop-ins (+ the one-launch Adam), same seeds: printed losses agree."""
+    from b200gan import launch
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "mini_convgan", "mini_convgan.py")
+    args = ["--epochs", "1", "--batch_size", "16", "--side", "32"]
+    _set_tf32(False)
+    ref = launch.run(script, args, iters=3, seed=3, stock=True, quiet=True)
+    ours = launch.run(script, args, iters=3, seed=3, stock=False, quiet=True)
+    assert type(ours["opt_g"]).__module__.endswith("b200gan.optim")
+    assert any(type(s).__name__ == "_ChainStep" for s in ours["D"].body._plan())
+    assert len(ref["history"]) == 3 and len(ours["history"]) == 3
+    for (dr, gr), (do, go) in zip(ref["history"], ours["history"]):
+        assert abs(do - dr) < 2e-3 * abs(dr) and abs(go - gr) < 2e-3 * abs(gr), (ref["history"], ours["history"])
