@@ -16,6 +16,10 @@ int simt_wgrad(int N, int H, int W, int Cg, int P, int Q, int Cd, int R, int S, 
                int pad_t, int pad_l, int pad_mode, int up, const float *xg, const float *dn,
                float *dw, cudaStream_t st);
 int simt_colsum(const float *x, float *out, int64_t M, int C, cudaStream_t st);
+// narrow_block.cu: shared-memory staged weight gradient of the narrow layers
+bool nb_wgrad_ok(const b200gan_conv_geom *g);
+int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
+                 cudaStream_t st);
 // conv_tc.cu / wgrad_tc.cu
 int tc_supported(const b200gan_conv_geom *g, int pass);
 int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x,
@@ -373,6 +377,9 @@ extern "C" int b200gan_conv2d_wgrad(const b200gan_conv_geom *g, const float *x, 
   if (a == B200GAN_ALGO_TC) {
     if (!tc_supported(g, 2)) B2_UNSUPPORTED("conv2d_wgrad: geometry not supported by the tcgen05 path");
     rc = tc_wgrad(g, x, dy, dw, workspace, st);
+  } else if (nb_wgrad_ok(g) && (int64_t)g->N * g->P * g->Q * g->K * g->C * g->R * g->S <= (int64_t)4e9) {
+    // narrow layers (C or K small): patch + dy tile staged in shared memory, all taps of a (c, 4k) set in registers
+    rc = nb_wgrad_run(g, nullptr, x, dy, dw, st);
   } else if (g->transposed) {
     rc = simt_wgrad(g->N, g->P, g->Q, g->K, g->H, g->W, g->C, g->R, g->S, g->stride, g->pad_t, g->pad_l,
                     B200GAN_PAD_ZERO, 1, dy, x, dw, st);

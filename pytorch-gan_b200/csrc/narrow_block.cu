@@ -647,11 +647,30 @@ extern "C" int b200gan_nb_dz(int32_t N, int64_t PQ, int32_t K, const float *g, c
   return B200GAN_OK;
 }
 
+namespace b200gan {
+// The weight-gradient kernel alone takes more geometries than the chain: any C <= 128, K a multiple of 4 up to 128.
+bool nb_wgrad_ok(const b200gan_conv_geom *g) {
+  if (!g || g->transposed || g->up != 1 || g->pad_mode != B200GAN_PAD_ZERO) return false;
+  if (g->stride != 1 && g->stride != 2) return false;
+  if (g->pad_t != g->pad_b || g->pad_l != g->pad_r) return false;
+  if (g->C < 1 || g->C > NB_MAXC || g->K < 4 || g->K > NB_MAXC || (g->K & 3)) return false;
+  if (g->R * g->S != 9 && g->R * g->S != 16) return false;
+  const int PR = g->R, PC = g->S;  // smallest tile (one pixel) must fit
+  return (size_t)(PR * PC * g->C + g->K + 2 * g->C + 8) * sizeof(float) <= 96 * 1024;
+}
+int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
+                 cudaStream_t st);
+}  // namespace b200gan
+
 extern "C" int b200gan_nb_wgrad(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz,
                                 float *dw, void *stream) {
-  B2_CHECK_ARG(b200gan_nb_supported(g), "nb_wgrad: unsupported geometry");
+  B2_CHECK_ARG(validate_geom(g) == B200GAN_OK && nb_wgrad_ok(g), "nb_wgrad: unsupported geometry");
   B2_CHECK_ARG(x && dz && dw, "nb_wgrad: null pointer");
-  cudaStream_t st = as_stream(stream);
+  return nb_wgrad_run(g, in_bn, x, dz, dw, as_stream(stream));
+}
+
+int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz,
+                          float *dw, cudaStream_t st) {
   B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)g->K * g->C * g->R * g->S * sizeof(float), st));
   if ((int64_t)g->N * g->P * g->Q == 0) return B200GAN_OK;
   NbWgrad p;
