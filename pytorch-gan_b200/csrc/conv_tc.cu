@@ -104,6 +104,8 @@ struct TcParams {
   float slope;
   int32_t rtf;
   float *y;
+  int32_t ksplit;    // > 1: the (tap, k-chunk) loop is split over `ksplit` CTAs; raw partial tiles are added into a zeroed
+                     // output with TMA reduce-stores (layers with few output pixels: pix2pix/models.py:62-73 at 1x1..8x8)
   long long *trace;  // bring-up: per-CTA clock64 timeline (64 slots per CTA) or nullptr
 };
 
@@ -141,7 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float *red = reinterpret_cast<float *>(tmem_ptr + 2);  // [4][BN][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ph = blockIdx.z;
+  const int ph = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
   const int ntile = blockIdx.y;
   const int BW = 1 << p.bw_log2, BH = 1 << p.bh_log2;
   int t = blockIdx.x;
@@ -152,7 +154,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2;
   const int n0 = tn * (TC_BM >> (p.bw_log2 + p.bh_log2));
   const int tap0 = p.tap_begin[ph];
-  const int iters = (p.tap_begin[ph + 1] - tap0) * p.kchunks;
+  const int iters_all = (p.tap_begin[ph + 1] - tap0) * p.kchunks;
+  const int it0 = (int)((long long)iters_all * ks / p.ksplit), it1 = (int)((long long)iters_all * (ks + 1) / p.ksplit);
+  const int iters = it1 - it0;   // >= 1: the host never asks for more splits than iterations
 
   if (threadIdx.x == 0) TC_TRACE(0);
   if (warp == 0 && lane == 0) {
@@ -178,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      int tap = 0, kc = 0;
+      int tap = it0 / p.kchunks, kc = it0 % p.kchunks;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t *sa = smem + stage * STAGE_BYTES;
@@ -239,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float *cs = p.chan_scale ? p.chan_scale + (int64_t)on * p.ldk + ntile * BN : nullptr;
     const int act = p.act, rtf = p.rtf;
     const float slope = p.slope;
+    const bool partial = p.ksplit > 1;  // raw partial sums: no bias / activation / statistics (the host checked)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     if (threadIdx.x == 64) TC_TRACE(40);
@@ -319,8 +324,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (threadIdx.x == 64) {
         TC_TRACE(44);
 #pragma unroll 1
-        for (int c = c0; c < c0 + ROUND; c += 32)
-          tma_store_5d(&tmY, smem + ((c - c0) >> 5) * TC_A_BYTES, p.out_dc[ph] + ntile * BN + c, w0, p.out_da[ph], h0, n0);
+        for (int c = c0; c < c0 + ROUND; c += 32) {
+          if (partial)
+            tma_reduce_add_5d(&tmY, smem + ((c - c0) >> 5) * TC_A_BYTES, p.out_dc[ph] + ntile * BN + c, w0, p.out_da[ph], h0,
+                              n0);
+          else
+            tma_store_5d(&tmY, smem + ((c - c0) >> 5) * TC_A_BYTES, p.out_dc[ph] + ntile * BN + c, w0, p.out_da[ph], h0, n0);
+        }
         TC_TRACE(45);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -733,10 +743,39 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   p.slope = ep ? ep->slope : 0.f;
   p.rtf = ep ? ep->round_tf32 : 0;
   p.y = y;
+  p.ksplit = 1;
+  double *deferred_stats = nullptr;
+  {
+    // few output tiles (deep U-Net layers at 1x1 .. 16x16 pixels): split the contraction so that the machine is used
+    static const bool allow = !(getenv("B200GAN_TC_KSPLIT") && atoi(getenv("B200GAN_TC_KSPLIT")) == 0);
+    const bool plain = !p.bias && !p.chan_scale && p.act == B200GAN_ACT_NONE && !p.rtf;
+    const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * ceil_div(N, BNn) * (Kout / BN) * nphase;
+    int min_iters = 1 << 30;
+    for (int z = 0; z < nphase; ++z) {
+      const int it = (tap_begin[z + 1] - tap_begin[z]) * p.kchunks;
+      if (it < min_iters) min_iters = it;
+    }
+    if (allow && plain && ctas < 148 && min_iters >= 16) {
+      int ks = (int)((2 * 148 + ctas - 1) / ctas);
+      if (ks > min_iters / 8) ks = min_iters / 8;
+      if (ks > 32) ks = 32;
+      if (ks >= 2) {
+        p.ksplit = ks;
+        if (p.stats) {  // partial tiles cannot carry the norm statistics: one extra pass over the (small) output
+          deferred_stats = p.stats;
+          p.stats = nullptr;
+        }
+      }
+    }
+  }
   p.trace = nullptr;
   if (const char *tv = getenv("B200GAN_TC_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(tv, nullptr, 0));
   B2_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)packedB % 16 == 0) && ((uintptr_t)y % 16 == 0),
                "tcgen05 conv: pointers must be 16-byte aligned");
+  if (p.ksplit > 1) {
+    const int64_t out_elems = phase_out ? (int64_t)N * (2 * Ho) * (2 * Wo) * ldk : (int64_t)N * Ho * Wo * ldk;
+    B2_CUDA(cudaMemsetAsync(y, 0, (size_t)out_elems * sizeof(float), st));
+  }
 
   CUtensorMap tmA, tmB, tmY;
   {
@@ -779,11 +818,22 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
     uint32_t box[2] = {TC_BK, (uint32_t)BN};
     if (int e = make_tmap_f32(&tmB, packedB, 2, dims, strides, box)) return e;
   }
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)nphase);
-  if (BN == 256) return launch_tc<256, 2>(tmA, tmB, tmY, p, grid, st);
-  if (BN == 128) return launch_tc<128, 3>(tmA, tmB, tmY, p, grid, st);
-  if (BN == 64) return launch_tc<64, 4>(tmA, tmB, tmY, p, grid, st);
-  return launch_tc<32, 4>(tmA, tmB, tmY, p, grid, st);
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)(nphase * p.ksplit));
+  int rc;
+  if (BN == 256) rc = launch_tc<256, 2>(tmA, tmB, tmY, p, grid, st);
+  else if (BN == 128) rc = launch_tc<128, 3>(tmA, tmB, tmY, p, grid, st);
+  else if (BN == 64) rc = launch_tc<64, 4>(tmA, tmB, tmY, p, grid, st);
+  else rc = launch_tc<32, 4>(tmA, tmB, tmY, p, grid, st);
+  if (rc == B200GAN_OK && deferred_stats) {
+    b200gan_norm_desc nd;
+    memset(&nd, 0, sizeof(nd));
+    nd.N = N;
+    nd.HW = phase_out ? 4 * Ho * Wo : Ho * Wo;
+    nd.C = ldk;
+    nd.per_sample = p.stats_per_sample;
+    rc = b200gan_norm_stats(&nd, y, deferred_stats, st);
+  }
+  return rc;
 }
 
 // Folded Upsample(2x)+Conv3x3 forward with all four phases in one CTA (conv_tc_up2_allphase_kernel).
