@@ -156,8 +156,11 @@ class ConvFn(torch.autograd.Function):
         return y
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, dy, *unused):
+        if torch.is_grad_enabled():
+            # autograd.grad(..., create_graph=True): the gradient penalty of a conv critic (stargan.py:142-161,
+            # dragan.py:144-167) differentiates THROUGH this backward -- build it from differentiable nodes
+            return _conv_backward_differentiable(ctx, dy)
         x, weight, y, chan_scale = ctx.saved_tensors
         spec, g = ctx.spec, ctx.g
         dy = _as_cl(dy)
@@ -187,6 +190,89 @@ class ConvFn(torch.autograd.Function):
             if not ctx.needs_input_grad[1]:
                 dw = None
         return dx, dw, db, None, None, None
+
+
+# ---- double backward through convolutions (conv-critic gradient penalties) ---------------------------
+# conv is bilinear in (x, w): the backward of its backward needs no new kernels.  With F = fprop(x, w):
+#   D = dgrad(dz, w)  (= dF/dx applied to dz):   dD/d(dz) applied to u = fprop(u, w),   dD/dw applied to u = wgrad(u, dz)
+#   W = wgrad(x, dz)  (= dF/dw applied to dz):   dW/dx applied to v  = dgrad(dz, v),    dW/d(dz) applied to v = fprop(x, v)
+def _plain_fprop(g, x, w):
+    tc = ops.tc_supported(g, 0)
+    kind = (PACK_TC_FPROP_UP2 if g.up == 2 else PACK_TC_FPROP) if tc else PACK_SIMT_FPROP
+    if g.transposed and not tc:
+        kind = PACK_SIMT_DGRAD
+    return ops.conv_fprop(g, x, ops.pack_weights(g, w, kind), ALGO_TC if tc else ALGO_SIMT)
+
+
+def _plain_dgrad(g, dz, w):
+    tc = ops.tc_supported(g, 1)
+    kind = (PACK_TC_DGRAD_UP2 if g.up == 2 else PACK_TC_DGRAD) if tc else PACK_SIMT_DGRAD
+    if g.transposed and not tc:
+        kind = PACK_SIMT_FPROP
+    return ops.conv_dgrad(g, dz, ops.pack_weights(g, w, kind), ALGO_TC if tc else ALGO_SIMT)
+
+
+def _plain_wgrad(g, x, dz, wshape):
+    return ops.conv_wgrad(g, x, dz, wshape, False, ALGO_SIMT if ops.Config.algo == "simt" else ALGO_AUTO)[0]
+
+
+class ConvDgradFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dz, weight, g):
+        ctx.g = g
+        ctx.save_for_backward(dz, weight)
+        return _plain_dgrad(g, _as_cl(dz.detach()), weight.detach())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u):
+        dz, weight = ctx.saved_tensors
+        g, u = ctx.g, _as_cl(u)
+        ddz = _plain_fprop(g, u, weight.detach()) if ctx.needs_input_grad[0] else None
+        dw = _plain_wgrad(g, u, _as_cl(dz.detach()), tuple(weight.shape)) if ctx.needs_input_grad[1] else None
+        return ddz, dw, None
+
+
+class ConvWgradFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dz, g, wshape):
+        ctx.g = g
+        ctx.save_for_backward(x, dz)
+        return _plain_wgrad(g, _as_cl(x.detach()), _as_cl(dz.detach()), wshape)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, v):
+        x, dz = ctx.saved_tensors
+        g, v = ctx.g, v.contiguous()
+        dx = _plain_dgrad(g, _as_cl(dz.detach()), v) if ctx.needs_input_grad[0] else None
+        ddz = _plain_fprop(g, _as_cl(x.detach()), v) if ctx.needs_input_grad[1] else None
+        return dx, ddz, None, None
+
+
+def _conv_backward_differentiable(ctx, dy):
+    x, weight, y, chan_scale = ctx.saved_tensors
+    spec, g = ctx.spec, ctx.g
+    if spec.up != 1 or spec.pad_mode != PAD_ZERO:
+        raise NotImplementedError("b200gan: double backward through a conv with a folded upsample / reflection padding")
+    dz = dy
+    if spec.act == ACT_LRELU:
+        dz = dz * torch.where(y > 0, 1.0, spec.slope)      # piecewise constant mask: no second-order term
+    elif spec.act == ACT_RELU:
+        dz = dz * (y > 0).to(dy.dtype)
+    elif spec.act == ACT_TANH:
+        dz = dz * (1 - y * y)                              # y is this node's (differentiable) output
+    elif spec.act == ACT_SIGMOID:
+        dz = dz * (y * (1 - y))
+    if chan_scale is not None:
+        dz = dz * chan_scale.view(chan_scale.shape[0], chan_scale.shape[1], 1, 1)
+        if spec.act in (ACT_TANH, ACT_SIGMOID):
+            raise NotImplementedError("b200gan: double backward through Dropout2d fused with tanh / sigmoid")
+    dx = ConvDgradFn.apply(dz, weight, g) if ctx.needs_input_grad[0] else None
+    dw = ConvWgradFn.apply(x, dz, g, tuple(weight.shape)) if ctx.needs_input_grad[1] else None
+    db = dz.sum((0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+    return dx, dw, db, None, None, None
+
 
 
 class NormFn(torch.autograd.Function):
