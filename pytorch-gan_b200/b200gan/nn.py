@@ -143,8 +143,13 @@ def _run_norm(norm, x, act=ACT_NONE, slope=0.0, stats=None, rtf_out=False, rtf_d
     return F.AffineActFn.apply(x, torch.cat([scale, shift]).detach(), act, slope)
 
 
+def _on_device(x):
+    """True for tensors the product path takes (CUDA).  A test hook: the CPU wiring tests replace it."""
+    return x.is_cuda
+
+
 def _gpu4d(x):
-    return x.dim() == 4 and x.is_cuda
+    return x.dim() == 4 and _on_device(x)
 
 
 # ---- leaf modules ----------------------------------------------------------------------------------
@@ -542,7 +547,7 @@ class Sequential(_T["Sequential"]):
     def forward(self, x):
         if _gpu2d_f32(x):
             return self._forward_2d(x)
-        if not (torch.is_tensor(x) and x.dim() == 4 and x.is_cuda and x.dtype == torch.float32):
+        if not (torch.is_tensor(x) and x.dim() == 4 and _on_device(x) and x.dtype == torch.float32):
             return super().forward(x)
         steps = self._plan()
         if all(isinstance(s, _LeafStep) for s in steps):
