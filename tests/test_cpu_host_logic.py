@@ -140,3 +140,24 @@ def test_algo_override_switches_the_planner_mirror():
         assert bnn._tc_like(conv, 1) and ops.tc_supported(g, 0)
     finally:
         ops.Config.algo = old
+
+
+def test_patch_dispatches_adam_and_resets_pack_caches_on_apply():
+    """patch(): torch.optim.Adam -> the one-launch Adam only when every parameter is a CUDA fp32 tensor (gan.py on CPU,
+    BASELINE config 0, keeps the stock optimizer); Module.apply drops the packed-weight caches (name-based init writes
+    parameters through .data, which does not bump the version counter the caches key on; dcgan.py:36-42)."""
+    import torch
+    import b200gan
+    from b200gan import nn as bnn
+    stock_adam = torch.optim.Adam
+    with b200gan.patched():
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Linear(4, 2))
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        assert type(opt) is stock_adam and isinstance(opt, torch.optim.Optimizer)       # CPU parameters: stock
+        assert isinstance(net[0], bnn.Conv2d)
+        net[0].__dict__["_b200_cache"] = object()
+        net.apply(lambda m: None)
+        assert "_b200_cache" not in net[0].__dict__
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda e: 1.0)         # cyclegan.py:93-101 still works
+        assert sched.get_last_lr() == [2e-4]
+    assert torch.optim.Adam is stock_adam and torch.nn.Module.apply.__qualname__ == "Module.apply"
