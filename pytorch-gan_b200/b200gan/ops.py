@@ -27,6 +27,8 @@ class Config:
     fuse_tail = os.environ.get("B200GAN_FUSE_TAIL", "1") not in ("", "0")
     # [Conv2d -> LeakyReLU -> Dropout2d -> BatchNorm2d] runs of narrow layers as the fused chain (csrc/narrow_block.cu)
     fuse_narrow_chain = os.environ.get("B200GAN_FUSE_CHAIN", "1") not in ("", "0")
+    # norm kernels: fixed-channel-group fast paths (csrc/norm.cu) and activation mask recomputed from x in backward
+    norm_fast = os.environ.get("B200GAN_NORM_FAST", "1") not in ("", "0")
 
 
 def _stream():

@@ -8,6 +8,7 @@
 // All kernels are HBM-bound streaming passes: float4 accesses along C, fp64 accumulation only
 // at the final atomic so that E[x^2]-E[x]^2 does not cancel catastrophically.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200gan {
 
@@ -358,7 +359,8 @@ norm_bwd_apply_v4_kernel(const float *__restrict__ dy, const float *__restrict__
 }
 
 static bool fast_path(const b200gan_norm_desc *d, const void *a, const void *b, const void *c, const void *e) {
-  if (d->C % 4 != 0) return false;
+  static const bool enabled = !(getenv("B200GAN_NORM_FAST") && atoi(getenv("B200GAN_NORM_FAST")) == 0);
+  if (!enabled || d->C % 4 != 0) return false;
   const int CV = d->C / 4;
   if (CV > 256 || 256 % CV != 0) return false;
   return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)e) & 15) == 0;
