@@ -6,8 +6,13 @@ echo "chain tests exit $?" >> gpurun_out/c3_tests_chain.log
 timeout 1500 python -m pytest tests -m gpu -q -s --deselect tests/test_gpu_chain.py > gpurun_out/c3_tests.log 2>&1
 echo "tests exit $?" >> gpurun_out/c3_tests.log
 if ! grep -q "tests exit 0" gpurun_out/c3_tests.log; then
-  B200GAN_TC_BN256=0 B200GAN_WG_PIX=32 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_models.py tests/test_gpu_dcgan.py -m gpu -q > gpurun_out/c3_tests_switches_off.log 2>&1
-  echo "switches-off exit $?" >> gpurun_out/c3_tests_switches_off.log
+  SUB="tests/test_gpu_ops.py tests/test_gpu_models.py tests/test_gpu_dcgan.py tests/test_gpu_tail.py"
+  B200GAN_TC_BN256=0 B200GAN_WG_PIX=32 B200GAN_TC_KSPLIT=0 timeout 600 python -m pytest $SUB -m gpu -q > gpurun_out/c3_tests_tc_switches_off.log 2>&1
+  echo "tc-switches-off exit $?" >> gpurun_out/c3_tests_tc_switches_off.log
+  B200GAN_NORM_FAST=0 timeout 600 python -m pytest $SUB -m gpu -q > gpurun_out/c3_tests_norm_fast_off.log 2>&1
+  echo "norm-fast-off exit $?" >> gpurun_out/c3_tests_norm_fast_off.log
+  B200GAN_FUSE_CHAIN=0 B200GAN_FUSE_TAIL=0 timeout 600 python -m pytest $SUB -m gpu -q > gpurun_out/c3_tests_fusions_off.log 2>&1
+  echo "fusions-off exit $?" >> gpurun_out/c3_tests_fusions_off.log
 fi
 timeout 300 python tools/profile_kernels.py > gpurun_out/c3_kernels.log 2>&1
 B200GAN_TC_BN256=0 B200GAN_WG_PIX=32 timeout 300 python tools/profile_kernels.py > gpurun_out/c3_kernels_switches_off.log 2>&1
