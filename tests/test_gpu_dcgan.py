@@ -165,11 +165,18 @@ def test_dcgan_training_steps_with_dropout_and_adam():
     og_r, od_r = ref_models.make_adam(g_ref.parameters()), ref_models.make_adam(d_ref.parameters())
     og, od = ref_models.make_adam(g.parameters()), ref_models.make_adam(d.parameters())
     init_params = [p.detach().clone() for p in list(g_ref.parameters()) + list(d_ref.parameters())]
+    # yardstick: the same three steps on stock torch with TF32 convolutions (the reference's default GPU path)
+    g_t, d_t = copy.deepcopy(g_ref), copy.deepcopy(d_ref)
+    og_t, od_t = ref_models.make_adam(g_t.parameters()), ref_models.make_adam(d_t.parameters())
     for step in range(3):
         z = ref_models.synthetic_z(batch, seed=10 + step).cuda()
         imgs = ref_models.synthetic_images(batch, 1, img_size, img_size, seed=10 + step).cuda()
         torch.manual_seed(100 + step)
         gl_r, dl_r, gen_r = ref_models.dcgan_step(g_ref, d_ref, og_r, od_r, imgs, z)
+        _set_tf32(True)
+        torch.manual_seed(100 + step)
+        ref_models.dcgan_step(g_t, d_t, og_t, od_t, imgs, z)
+        _set_tf32(False)
         torch.manual_seed(100 + step)
         gl, dl, gen = train.dcgan_step(g, d, og, od, imgs, z)
         assert abs(gl.item() - gl_r.item()) < TOL * abs(gl_r.item()), step
@@ -177,16 +184,17 @@ def test_dcgan_training_steps_with_dropout_and_adam():
         assert rel_err(gen, gen_r) < 5 * TOL, step   # G parameters already carry 1-2 steps of TF32-level gradient noise
     import b200gan
     skip = {"conv_blocks.2.bias", "conv_blocks.6.bias"}  # Conv -> BatchNorm directly (dcgan.py:55-56,59-60)
-    step_tol = 2e-2 if b200gan.Config.algo == "simt" else 0.25  # stock torch TF32 deviates by the same order
-    for (k, po), (_, pr), p0 in zip(list(g.named_parameters()) + list(d.named_parameters()),
-                                    list(g_ref.named_parameters()) + list(d_ref.named_parameters()),
-                                    init_params):
+    for (k, po), (_, pr), (_, pt), p0 in zip(list(g.named_parameters()) + list(d.named_parameters()),
+                                             list(g_ref.named_parameters()) + list(d_ref.named_parameters()),
+                                             list(g_t.named_parameters()) + list(d_t.named_parameters()),
+                                             init_params):
         if k in skip:
             continue
         if p0.abs().max().item() == 0.0:
-            # zero-initialised BatchNorm biases: the value after 3 steps IS the sum of the Adam steps, so it
-            # carries the gradient-level deviation (TF32 through BatchNorm backward, see module docstring)
-            assert rel_err(po - p0, pr - p0) < step_tol, k
+            # zero-initialised BatchNorm biases: the value after 3 steps IS the sum of the Adam steps, so it carries
+            # the gradient-level deviation (TF32 through BatchNorm backward).  Bound: 1.5x what stock TF32 shows here.
+            step_tol = 2e-2 if b200gan.Config.algo == "simt" else max(2e-2, 1.5 * rel_err(pt - p0, pr - p0))
+            assert rel_err(po - p0, pr - p0) < step_tol, (k, step_tol)
         else:
             assert rel_err(po, pr) < 2 * TOL, k
 
