@@ -392,14 +392,23 @@ def time_job(torch, dist, args, stock, dev, world, rank, local, steps, warmup, c
     dev_pools = [[t.to(dev) for t in p] for p in pools]
     torch.manual_seed(99 + rank)  # dropout streams differ per rank
     calls0 = _lib.CALLS
+    graph_error = None
     if args.no_graph:
         runner = lambda *xs: step(*[x.to(dev, non_blocking=True) for x in xs])  # noqa: E731
         for _ in range(3):
             runner(*[p[0] for p in dev_pools])
         calls_per_step = (_lib.CALLS - calls0) // 3
     else:
-        runner = train.GraphedStep(step, [p[0] for p in dev_pools], warmup=3)
-        calls_per_step = (_lib.CALLS - calls0) // 4  # 3 warm-up + 1 captured executions
+        try:
+            runner = train.GraphedStep(step, [p[0] for p in dev_pools], warmup=3)
+            calls_per_step = (_lib.CALLS - calls0) // 4  # 3 warm-up + 1 captured executions
+        except Exception as e:  # a step that cannot be captured is still measured (eagerly) and says so
+            graph_error = f"{type(e).__name__}: {e}"[:300]
+            torch.cuda.synchronize()
+            runner = lambda *xs: step(*[x.to(dev, non_blocking=True) for x in xs])  # noqa: E731
+            c1 = _lib.CALLS
+            runner(*[p[0] for p in dev_pools])
+            calls_per_step = _lib.CALLS - c1
 
     def barrier():
         if world > 1:
@@ -439,7 +448,7 @@ def time_job(torch, dist, args, stock, dev, world, rank, local, steps, warmup, c
     ms, ms_e2e = t.tolist()
     h2d = sum(p[0].numel() * 4 for p in pools)
     res = dict(ms_per_step=ms / steps, ms_per_step_e2e=ms_e2e / steps, losses=losses, clocks=clk, h2d=h2d, d2h=d2h,
-               calls_per_step=calls_per_step)
+               calls_per_step=calls_per_step, graph_error=graph_error)
     del runner, step
     return res
 
@@ -530,7 +539,8 @@ def run_gpu(args):
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": cfg["workload"], "global_batch": B * world, "parallelism": f"dp{world}",
-                   "cuda_graph": not args.no_graph,
+                   "cuda_graph": not args.no_graph and res["graph_error"] is None,
+                   "cuda_graph_error": res["graph_error"],
                    "l2": "per-step working set of activations exceeds the 126 MB L2; a pool of distinct input batches; "
                          "no explicit flush",
                    "algo": "stock" if stock else b200gan.Config.algo},
