@@ -518,10 +518,10 @@ class NbConvFn(torch.autograd.Function):
             if in_edge is not None:
                 in_edge.sums = sums
                 c = g.C
-                if ctx.needs_input_grad[4]:
-                    dgamma = sums[c:].float()
-                if ctx.needs_input_grad[5]:
-                    dbeta = sums[:c].float()
+                if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+                    dgb = sums.float()          # one conversion kernel for both parameter gradients
+                    dgamma = dgb[c:] if ctx.needs_input_grad[4] else None
+                    dbeta = dgb[:c] if ctx.needs_input_grad[5] else None
         return gx, dw, db, None, dgamma, dbeta, None, None, None, None, None, None, None
 
 
@@ -545,8 +545,11 @@ class NbTailFn(torch.autograd.Function):
         g, sums = ops.nb_tail_bwd(a, ctx.edge, dout, ctx.nchw)
         ctx.edge.sums = sums
         c = a.shape[1]
-        dgamma = sums[c:].float() if ctx.needs_input_grad[1] else None
-        dbeta = sums[:c].float() if ctx.needs_input_grad[2] else None
+        dgamma = dbeta = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dgb = sums.float()
+            dgamma = dgb[c:] if ctx.needs_input_grad[1] else None
+            dbeta = dgb[:c] if ctx.needs_input_grad[2] else None
         return g, dgamma, dbeta, None, None, None, None, None, None
 
 
