@@ -285,7 +285,8 @@ static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
   pl.Ho = up2 ? g->H : (g->transposed ? g->H : g->P);
   pl.Wo = up2 ? g->W : (g->transposed ? g->W : g->Q);
   // 64-pixel stages for the 64-wide B operand (two CTAs per SM still fit with two stages); 128-wide keeps 32
-  pl.pix = (pl.NB == 64 && wg_pix_pref() == 64 && (int64_t)pl.Ho * pl.Wo >= 64) ? 64 : 32;
+  static const bool pix64_wide = getenv("B200GAN_WG_PIX128") && atoi(getenv("B200GAN_WG_PIX128")) == 64;  // experiment
+  pl.pix = ((pl.NB == 64 || (pl.NB == 128 && pix64_wide)) && wg_pix_pref() == 64 && (int64_t)pl.Ho * pl.Wo >= 64) ? 64 : 32;
   const int pl2 = pl.pix == 64 ? 6 : 5;
   pl.bwl = ilog2c(pl.Wo);
   if (pl.bwl > pl2) pl.bwl = pl2;
@@ -407,7 +408,8 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   }
   B2_CUDA(cudaMemsetAsync(ws, 0, (size_t)pl.njobs * pl.mtotal * pl.ldn * sizeof(float), st));
   dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
-  int rc = pl.NB == 128 ? launch_wg<128, 3, 32>(tmX, tmY, tmP, p, grid, st)
+  int rc = pl.NB == 128 ? (pl.pix == 64 ? launch_wg<128, 2, 64>(tmX, tmY, tmP, p, grid, st)
+                                        : launch_wg<128, 3, 32>(tmX, tmY, tmP, p, grid, st))
            : pl.NB == 64 ? (pl.pix == 64 ? launch_wg<64, 2, 64>(tmX, tmY, tmP, p, grid, st)
                                          : launch_wg<64, 4, 32>(tmX, tmY, tmP, p, grid, st))
                          : launch_wg<32, 4, 32>(tmX, tmY, tmP, p, grid, st);

@@ -16,6 +16,7 @@ if ! grep -q "tests exit 0" gpurun_out/c3_tests.log; then
 fi
 timeout 300 python tools/profile_kernels.py > gpurun_out/c3_kernels.log 2>&1
 B200GAN_TC_BN256=0 B200GAN_WG_PIX=32 timeout 300 python tools/profile_kernels.py > gpurun_out/c3_kernels_switches_off.log 2>&1
+B200GAN_WG_PIX128=64 timeout 300 python tools/profile_kernels.py > gpurun_out/c3_kernels_wgpix128.log 2>&1
 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/c3_bench.json 2> gpurun_out/c3_bench.err
 timeout 300 python bench.py --config wgan_gp --no-cpu-baseline > gpurun_out/c3_bench_wgan_gp.json 2> gpurun_out/c3_bench_wgan_gp.err
 NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
