@@ -129,7 +129,7 @@ class ConvFn(torch.autograd.Function):
         g, _ = ops.make_geom(tuple(x.shape), tuple(weight.shape), spec.stride, spec.pads, spec.pad_mode, spec.up,
                              spec.transposed)
         w = weight.detach()
-        if ops.tc_supported(g, 0):
+        if ops.tc_supported(g, 0) and not (g.K < 32 and chan_scale is not None):
             algo = ALGO_TC
             packed = cache.get(g, w, PACK_TC_FPROP_UP2 if spec.up == 2 else PACK_TC_FPROP)
         else:

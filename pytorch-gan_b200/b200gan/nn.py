@@ -74,14 +74,20 @@ def _conv_ok(m):
     return True
 
 
-def _tc_like(conv, up):
-    """Static mirror of tc_supported() used to decide where TF32 rounding of operands pays."""
+def _tc_like(conv, up, full=False):
+    """Static mirror of tc_supported() used to decide where TF32 rounding of operands pays.  full: every pass (forward,
+    data gradient, weight gradient) is on the tensor cores, not just the forward."""
     if ops.Config.algo == "simt":
         return False
     if up == 2:
         return (not isinstance(conv, _T["ConvTranspose2d"]) and conv.stride[0] == 1 and conv.in_channels % 32 == 0
                 and conv.out_channels % 64 == 0)
-    return conv.stride[0] in (1, 2) and conv.in_channels % 32 == 0 and conv.out_channels % 32 == 0
+    if conv.stride[0] in (1, 2) and conv.in_channels % 32 == 0 and conv.out_channels % 32 == 0:
+        return True
+    # fewer than 32 output channels (cyclegan/models.py:82: Conv2d(64, 3, 7)): the FORWARD runs on tcgen05 (weight rows
+    # zero-padded to 32 by TMA), the gradients on the fp32 kernels
+    return (full is False and not isinstance(conv, _T["ConvTranspose2d"]) and conv.stride[0] == 1
+            and conv.in_channels % 32 == 0 and conv.out_channels < 32)
 
 
 def _dropout2d_scale(x_shape, p, device):
@@ -280,10 +286,10 @@ class _ConvStep:
         self.rtf_dz = False
         self.next_norm = None
 
-    def tc_like(self):
+    def tc_like(self, full=False):
         if self.pad_mode == PAD_REFLECT and self.up != 1:
             return False
-        return _tc_like(self.conv, self.up)
+        return _tc_like(self.conv, self.up, full)
 
 
 class _NormStep:
@@ -435,6 +441,8 @@ def _build_plan(mods):
         if isinstance(s, _ConvStep) and s.tc_like():
             if k > 0 and isinstance(steps[k - 1], (_ConvStep, _NormStep)):
                 steps[k - 1].rtf_out = True
+            if not s.tc_like(full=True):
+                continue        # forward only: the gradients of this conv run in fp32
             s.rtf_dz = True
             # A conv with a fused epilogue (activation / Dropout2d) rounds its dz in epilogue_bwd and takes its bias
             # gradient from the unrounded values; only a conv WITHOUT epilogue consumes the norm's dx directly, and

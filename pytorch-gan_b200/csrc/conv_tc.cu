@@ -104,6 +104,8 @@ struct TcParams {
   float slope;
   int32_t rtf;
   float *y;
+  int32_t narrow_k;  // 0, or the real number of output channels (< 32) of a layer whose B rows are zero-padded to 32 by
+                     // TMA out-of-bounds fill (cyclegan/models.py:82, Conv2d(64, 3, 7)): direct stores, no TMA store
   int32_t ksplit;    // > 1: the (tap, k-chunk) loop is split over `ksplit` CTAs; raw partial tiles are added into a zeroed
                      // output with TMA reduce-stores (layers with few output pixels: pix2pix/models.py:62-73 at 1x1..8x8)
   long long *trace;  // bring-up: per-CTA clock64 timeline (64 slots per CTA) or nullptr
@@ -191,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (it < 16) TC_TRACE(2 + it);
         mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
         tma_load_5d(sa, &tmA, &full[stage], tp.dc + kc * TC_BK, w0 + tp.dw, tp.da, h0 + tp.dh, n0);
-        tma_load_2d(sb, &tmB, &full[stage], kc * TC_BK, tp.bt * p.kout_total + ntile * BN);
+        tma_load_3d(sb, &tmB, &full[stage], kc * TC_BK, ntile * BN, tp.bt);
         if (++kc == p.kchunks) {
           kc = 0;
           ++tap;
@@ -264,7 +266,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (threadIdx.x == 64) TC_TRACE(49 + ((c >> 5) & 3) * 3);
         // every option is tested ONCE per chunk, never per element: a switch inside the unrolled element loop
         // becomes 32 indirect branches into a 50 KB body and costs ~200 cycles each (measured: 6.5k cycles/chunk)
-        if (p.bias) {
+        if (p.bias && p.narrow_k) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < p.narrow_k) v[j] += __ldg(p.bias + j);
+        } else if (p.bias) {
           const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + ntile * BN + c);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -297,7 +303,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
         }
-        {
+        if (p.narrow_k) {
+          // fewer than 32 real output channels: one pixel's channels are 4..124 contiguous bytes, written directly
+          if (valid) {
+            float *dst = p.y + ((int64_t)(on * p.Ho + oh) * p.Wo + ow) * p.narrow_k;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < p.narrow_k) dst[j] = v[j];
+          }
+        } else {
           uint8_t *row = smem + (((c - c0) >> 5)) * TC_A_BYTES + m * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -321,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (threadIdx.x == 64) TC_TRACE(43);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the async (TMA) proxy
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
+      if (threadIdx.x == 64 && !p.narrow_k) {
         TC_TRACE(44);
 #pragma unroll 1
         for (int c = c0; c < c0 + ROUND; c += 32) {
@@ -664,7 +678,9 @@ int tc_supported(const b200gan_conv_geom *g, int pass) {
   if (g->stride != 1 && g->stride != 2) return 0;
   const int cin = pass == 0 ? g->C : g->K;   // contraction channels
   const int cout = pass == 0 ? g->K : g->C;  // produced channels
-  if (cin % 32 != 0 || cout % 32 != 0 || 2 * cin > 32767) return 0;
+  // fewer than 32 produced channels: only the plain stride-1 gather form (Conv2d forward), B rows zero-padded by TMA
+  const bool narrow = cout < 32 && pass == 0 && !g->transposed && g->up == 1 && g->stride == 1;
+  if (cin % 32 != 0 || (cout % 32 != 0 && !narrow) || 2 * cin > 32767) return 0;
   if (g->R * g->S > 49 || g->R > 15 || g->S > 15 || g->pad_t > 15 || g->pad_l > 15) return 0;
   if (g->up == 2) {
     if (g->transposed || g->stride != 1) return 0;
@@ -700,6 +716,9 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
                   int btaps, int nphase, const int *tap_begin, const TcTap *taps, int Ho, int Wo, bool phase_out,
                   const int *out_dc, const int *out_da, int ldk, const b200gan_epilogue *ep, float *y,
                   cudaStream_t st) {
+  const int narrow_k = Kout < 32 ? Kout : 0;
+  const int Kreal = Kout;
+  if (narrow_k) Kout = 32;  // MMA N = 32; rows >= Kreal of every B box are TMA out-of-bounds zeros
   int BN = (Kout % 128 == 0) ? 128 : (Kout % 64 == 0 ? 64 : 32);
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -743,8 +762,17 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   p.slope = ep ? ep->slope : 0.f;
   p.rtf = ep ? ep->round_tf32 : 0;
   p.y = y;
+  p.narrow_k = narrow_k;
+  if (narrow_k) {
+    B2_CHECK_ARG(!phase_in && !phase_out && nphase == 1, "tcgen05 conv: narrow output only in the plain gather form");
+    B2_CHECK_ARG(!p.chan_scale, "tcgen05 conv: Dropout2d scale with fewer than 32 output channels");
+  }
   p.ksplit = 1;
   double *deferred_stats = nullptr;
+  if (narrow_k && p.stats) {  // statistics of a narrow layer: separate pass
+    deferred_stats = p.stats;
+    p.stats = nullptr;
+  }
   {
     // few output tiles (deep U-Net layers at 1x1 .. 16x16 pixels): split the contraction so that the machine is used
     static const bool allow = !(getenv("B200GAN_TC_KSPLIT") && atoi(getenv("B200GAN_TC_KSPLIT")) == 0);
@@ -755,7 +783,7 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
       const int it = (tap_begin[z + 1] - tap_begin[z]) * p.kchunks;
       if (it < min_iters) min_iters = it;
     }
-    if (allow && plain && ctas < 148 && min_iters >= 16) {
+    if (allow && plain && !narrow_k && ctas < 148 && min_iters >= 16) {
       int ks = (int)((2 * 148 + ctas - 1) / ctas);
       if (ks > min_iters / 8) ks = min_iters / 8;
       if (ks > 32) ks = 32;
@@ -778,7 +806,7 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
   }
 
   CUtensorMap tmA, tmB, tmY;
-  {
+  if (!narrow_k) {
     // output map: box = one 32-channel chunk of the 128-pixel tile; TMA clips rows outside the tensor
     uint64_t dims[5], strides[4];
     uint32_t box[5] = {TC_BK, (uint32_t)BW, 1, (uint32_t)BH, (uint32_t)BNn};
@@ -812,11 +840,13 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
     }
     if (int e = make_tmap_f32(&tmA, in, 5, dims, strides, box)) return e;
   }
+  if (narrow_k) tmY = tmA;  // never used for stores (rows of < 32 channels cannot be a TMA box): any valid descriptor
   {
-    uint64_t dims[2] = {(uint64_t)Cc, (uint64_t)btaps * Kout};
-    uint64_t strides[1] = {(uint64_t)Cc * 4};
-    uint32_t box[2] = {TC_BK, (uint32_t)BN};
-    if (int e = make_tmap_f32(&tmB, packedB, 2, dims, strides, box)) return e;
+    // weights [tap][Kreal][Cc] as a rank-3 map: a box never runs into the next tap, rows beyond Kreal are zero fill
+    uint64_t dims[3] = {(uint64_t)Cc, (uint64_t)Kreal, (uint64_t)btaps};
+    uint64_t strides[2] = {(uint64_t)Cc * 4, (uint64_t)Kreal * Cc * 4};
+    uint32_t box[3] = {TC_BK, (uint32_t)BN, 1};
+    if (int e = make_tmap_f32(&tmB, packedB, 3, dims, strides, box)) return e;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)(nphase * p.ksplit));
   int rc;
