@@ -84,11 +84,15 @@ def test_pix2pix_and_cyclegan_hot_layers_are_tensor_core_eligible():
     for xs, ws, stride, pad, up, tr in cases:
         g, _ = _geom(xs, ws, stride, pad, up, tr)
         assert ops.tc_supported(g, 0) and ops.tc_supported(g, 1), (xs, ws)
-    # edge layers stay on the SIMT path: 3-channel images, the 1-channel PatchGAN head
-    for xs, ws, stride, pad in [((1, 6, 256, 256), (64, 6, 4, 4), 2, 1), ((1, 512, 17, 17), (1, 512, 4, 4), 1, 1),
-                                ((2, 3, 70, 70), (64, 3, 7, 7), 1, 0)]:
+    # 3-channel image inputs stay on the fp32 path
+    for xs, ws, stride, pad in [((1, 6, 256, 256), (64, 6, 4, 4), 2, 1), ((2, 3, 70, 70), (64, 3, 7, 7), 1, 0)]:
         g, _ = _geom(xs, ws, stride, pad)
         assert not ops.tc_supported(g, 0)
+    # few-output-channel layers: forward on tcgen05 (narrow form), gradients fp32 -- the 1-channel PatchGAN head
+    # (pix2pix/models.py:127) and the 3-channel output conv (cyclegan/models.py:82, on the reflection-padded map)
+    for xs, ws, stride, pad in [((1, 512, 17, 17), (1, 512, 4, 4), 1, 1), ((2, 64, 70, 70), (3, 64, 7, 7), 1, 0)]:
+        g, _ = _geom(xs, ws, stride, pad)
+        assert ops.tc_supported(g, 0) and not ops.tc_supported(g, 1) and not ops.tc_supported(g, 2)
 
 
 def test_geometry_validation_and_error_reporting():
