@@ -22,5 +22,6 @@ timeout 300 python bench.py --config wgan_gp --no-cpu-baseline > gpurun_out/c3_b
 NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 timeout 600 $NCU --log-file gpurun_out/c3_launches.csv python bench.py --steps 2 --warmup 1 --no-gpu-reference --no-roofline --no-cpu-baseline > gpurun_out/c3_ncu_bench.log 2>&1
 timeout 900 $NCU --log-file gpurun_out/c3_launches_pix2pix.csv python bench.py --config pix2pix --steps 1 --warmup 1 --no-gpu-reference --no-roofline --no-cpu-baseline > gpurun_out/c3_ncu_pix2pix.log 2>&1
+timeout 900 $NCU --log-file gpurun_out/c3_launches_cyclegan.csv python bench.py --config cyclegan --steps 1 --warmup 1 --no-gpu-reference --no-roofline --no-cpu-baseline > gpurun_out/c3_ncu_cyclegan.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tail_ -c 6 -o gpurun_out/c3_tail_prof python bench.py --steps 2 --warmup 1 --no-gpu-reference --no-cpu-baseline > gpurun_out/c3_ncu_tail.log 2>&1
 tail -15 gpurun_out/c3_tests_chain.log; tail -8 gpurun_out/c3_tests.log; cut -c1-300 gpurun_out/c3_bench.json
