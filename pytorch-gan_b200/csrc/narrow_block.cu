@@ -280,7 +280,9 @@ struct NbWgrad {
   int TR, TQ, tiles_r, tiles_q;  // output-pixel tile and tiles per image
   int PR, PC;                    // patch rows / columns = (TR-1)*stride + R, (TQ-1)*stride + S
   int SPB, PS;                   // sets per block (<= 256), pixel split = 256 / SPB
-  int nsets;                     // C * K/4
+  int nsets;                     // C * K/4 (* R in row mode)
+  int row_mode;                  // 1: a set owns ONE filter row (TAPS = S): 7x7 filters (cyclegan/models.py:50)
+  int reflect;                   // 1: the virtual input is reflection-padded (cyclegan/models.py:49) instead of zero-padded
 };
 // thread = set (c, kg: 4 output channels) x all TAPS taps in registers, and one of PS pixel phases.
 // grid = (persistent blocks over tiles, set chunks).  dynamic smem: patch [PR][PC][C] | dz tile [TR*TQ][K] | sc, sh [C]
@@ -303,7 +305,9 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   const int set_local = tid % p.SPB, psplit = tid / p.SPB;
   const int set = blockIdx.y * p.SPB + set_local;
   const bool set_ok = set < p.nsets;
-  const int c = set_ok ? set % p.C : 0, kg = set_ok ? set / p.C : 0;
+  const int K4 = p.K >> 2;
+  const int c = set_ok ? set % p.C : 0, kg = set_ok ? (set / p.C) % K4 : 0;
+  const int r_own = (set_ok && p.row_mode) ? set / (p.C * K4) : 0;   // filter row of this set (row mode)
   float acc[TAPS][4];
 #pragma unroll
   for (int t = 0; t < TAPS; ++t)
@@ -313,7 +317,7 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   const int tile_px = p.TR * p.TQ;
   int toff[TAPS];  // offset of tap t inside the patch, relative to the pixel's top-left element
 #pragma unroll
-  for (int t = 0; t < TAPS; ++t) toff[t] = ((t / p.S) * p.PC + (t % p.S)) * p.C;
+  for (int t = 0; t < TAPS; ++t) toff[t] = p.row_mode ? (r_own * p.PC + t) * p.C : ((t / p.S) * p.PC + (t % p.S)) * p.C;
   __syncthreads();
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tq = tile % p.tiles_q;
@@ -326,13 +330,16 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
       const int cc = i % p.C;
       const int pc = (i / p.C) % p.PC;
       const int pr = i / (p.C * p.PC);
-      const int ih = h0 + pr, iw = w0 + pc;
+      int ih = h0 + pr, iw = w0 + pc;
+      if (p.reflect) {   // rows / columns of tiles that hang over the output edge may reflect twice: clamp afterwards
+        ih = reflect_idx(ih, p.H);
+        iw = reflect_idx(iw, p.W);
+      }
       float v = 0.f;
       if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
         v = fmaf(__ldg(p.x + ((int64_t)(n * p.H + ih) * p.W + iw) * p.C + cc), sc_s[cc], sh_s[cc]);
       x_s[i] = v;
     }
-    const int K4 = p.K >> 2;
     for (int i = tid; i < tile_px * K4; i += 256) {
       const int k4 = i % K4, pix = i / K4;
       const int lr = pix / p.TQ, lq = pix % p.TQ;
@@ -363,7 +370,7 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   if (set_ok) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float *dst = p.dw + ((int64_t)(kg * 4 + j) * p.C + c) * TAPS;
+      float *dst = p.dw + ((int64_t)(kg * 4 + j) * p.C + c) * (p.R * p.S) + r_own * p.S;   // r_own == 0 in full mode
 #pragma unroll
       for (int t = 0; t < TAPS; ++t) atomicAdd(dst + t, acc[t][j]);
     }
@@ -650,11 +657,12 @@ extern "C" int b200gan_nb_dz(int32_t N, int64_t PQ, int32_t K, const float *g, c
 namespace b200gan {
 // The weight-gradient kernel alone takes more geometries than the chain: any C <= 128, K a multiple of 4 up to 128.
 bool nb_wgrad_ok(const b200gan_conv_geom *g) {
-  if (!g || g->transposed || g->up != 1 || g->pad_mode != B200GAN_PAD_ZERO) return false;
+  if (!g || g->transposed || g->up != 1) return false;
+  if (g->pad_mode != B200GAN_PAD_ZERO && g->pad_mode != B200GAN_PAD_REFLECT) return false;
   if (g->stride != 1 && g->stride != 2) return false;
   if (g->pad_t != g->pad_b || g->pad_l != g->pad_r) return false;
   if (g->C < 1 || g->C > NB_MAXC || g->K < 4 || g->K > NB_MAXC || (g->K & 3)) return false;
-  if (g->R * g->S != 9 && g->R * g->S != 16) return false;
+  if (g->R * g->S != 9 && g->R * g->S != 16 && !(g->R == 7 && g->S == 7)) return false;
   const int PR = g->R, PC = g->S;  // smallest tile (one pixel) must fit
   return (size_t)(PR * PC * g->C + g->K + 2 * g->C + 8) * sizeof(float) <= 96 * 1024;
 }
@@ -693,7 +701,9 @@ int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn
   p.tiles_q = ceil_div(g->Q, p.TQ);
   p.PR = (p.TR - 1) * g->stride + g->R;
   p.PC = (p.TQ - 1) * g->stride + g->S;
-  p.nsets = g->C * (g->K / 4);
+  p.row_mode = (g->R * g->S > 16) ? 1 : 0;
+  p.reflect = g->pad_mode == B200GAN_PAD_REFLECT ? 1 : 0;
+  p.nsets = g->C * (g->K / 4) * (p.row_mode ? g->R : 1);
   int spb = 256;
   if (p.nsets < 256) {  // fewer sets than threads: several threads share a set and split the pixels of a tile
     spb = 1;
@@ -708,9 +718,12 @@ int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn
   if (gx < 8) gx = 8;
   if (gx > ntiles) gx = ntiles;
   const int taps = g->R * g->S;
-  static std::atomic<uint64_t> done9{0}, done16{0};
+  static std::atomic<uint64_t> done9{0}, done16{0}, done7{0};
   dim3 grid((unsigned)gx, (unsigned)nchunks);
-  if (taps == 9) {
+  if (p.row_mode) {
+    if (int e = ensure_dynamic_smem(nbk_wgrad_kernel<7>, 96 * 1024, done7)) return e;
+    nbk_wgrad_kernel<7><<<grid, 256, smem, st>>>(p);
+  } else if (taps == 9) {
     if (int e = ensure_dynamic_smem(nbk_wgrad_kernel<9>, 96 * 1024, done9)) return e;
     nbk_wgrad_kernel<9><<<grid, 256, smem, st>>>(p);
   } else {
