@@ -292,20 +292,20 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   extern __shared__ __align__(16) float nsm[];
   float *x_s = nsm;
   float *dz_s = x_s + ((p.PR * p.PC * p.C + 3) & ~3);
-  float *sc_s = dz_s + p.TR * p.TQ * p.K;
+  float *sc_s = dz_s + p.TR * p.TQ * (((p.K + 3) >> 2) << 2);
   float *sh_s = sc_s + p.C;
   const int tid = threadIdx.x;
   const bool has_in = p.in_bn.stats != nullptr;
-  if (tid < p.C) {
+  for (int cc = tid; cc < p.C; cc += 256) {
     float mean, rstd, sc = 1.f, sh = 0.f;
-    if (has_in) nb_bn_consts(p.in_bn, p.C, tid, mean, rstd, sc, sh);
-    sc_s[tid] = sc;
-    sh_s[tid] = sh;
+    if (has_in) nb_bn_consts(p.in_bn, p.C, cc, mean, rstd, sc, sh);
+    sc_s[cc] = sc;
+    sh_s[cc] = sh;
   }
   const int set_local = tid % p.SPB, psplit = tid / p.SPB;
   const int set = blockIdx.y * p.SPB + set_local;
   const bool set_ok = set < p.nsets;
-  const int K4 = p.K >> 2;
+  const int K4 = (p.K + 3) >> 2, KP = K4 * 4;   // output channels padded to a multiple of 4 inside the dz tile
   const int c = set_ok ? set % p.C : 0, kg = set_ok ? (set / p.C) % K4 : 0;
   const int r_own = (set_ok && p.row_mode) ? set / (p.C * K4) : 0;   // filter row of this set (row mode)
   float acc[TAPS][4];
@@ -340,19 +340,30 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
         v = fmaf(__ldg(p.x + ((int64_t)(n * p.H + ih) * p.W + iw) * p.C + cc), sc_s[cc], sh_s[cc]);
       x_s[i] = v;
     }
-    for (int i = tid; i < tile_px * K4; i += 256) {
-      const int k4 = i % K4, pix = i / K4;
-      const int lr = pix / p.TQ, lq = pix % p.TQ;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p0 + lr < p.P && q0 + lq < p.Q)
-        v = __ldg(reinterpret_cast<const float4 *>(p.dz + ((int64_t)(n * p.P + p0 + lr) * p.Q + q0 + lq) * p.K) + k4);
-      reinterpret_cast<float4 *>(dz_s)[i] = v;
+    if ((p.K & 3) == 0) {
+      for (int i = tid; i < tile_px * K4; i += 256) {
+        const int k4 = i % K4, pix = i / K4;
+        const int lr = pix / p.TQ, lq = pix % p.TQ;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p0 + lr < p.P && q0 + lq < p.Q)
+          v = __ldg(reinterpret_cast<const float4 *>(p.dz + ((int64_t)(n * p.P + p0 + lr) * p.Q + q0 + lq) * p.K) + k4);
+        reinterpret_cast<float4 *>(dz_s)[i] = v;
+      }
+    } else {
+      for (int i = tid; i < tile_px * KP; i += 256) {
+        const int k = i % KP, pix = i / KP;
+        const int lr = pix / p.TQ, lq = pix % p.TQ;
+        float v = 0.f;
+        if (k < p.K && p0 + lr < p.P && q0 + lq < p.Q)
+          v = __ldg(p.dz + ((int64_t)(n * p.P + p0 + lr) * p.Q + q0 + lq) * p.K + k);
+        dz_s[i] = v;
+      }
     }
     __syncthreads();
     if (set_ok) {
       for (int pix = psplit; pix < tile_px; pix += p.PS) {
         const int lr = pix / p.TQ, lq = pix % p.TQ;
-        const float4 d4 = *reinterpret_cast<const float4 *>(dz_s + pix * p.K + kg * 4);
+        const float4 d4 = *reinterpret_cast<const float4 *>(dz_s + pix * KP + kg * 4);
         const float *xb = x_s + ((lr * p.stride) * p.PC + lq * p.stride) * p.C + c;
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) {
@@ -370,6 +381,7 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   if (set_ok) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      if (kg * 4 + j >= p.K) break;
       float *dst = p.dw + ((int64_t)(kg * 4 + j) * p.C + c) * (p.R * p.S) + r_own * p.S;   // r_own == 0 in full mode
 #pragma unroll
       for (int t = 0; t < TAPS; ++t) atomicAdd(dst + t, acc[t][j]);
@@ -661,7 +673,8 @@ bool nb_wgrad_ok(const b200gan_conv_geom *g) {
   if (g->pad_mode != B200GAN_PAD_ZERO && g->pad_mode != B200GAN_PAD_REFLECT) return false;
   if (g->stride != 1 && g->stride != 2) return false;
   if (g->pad_t != g->pad_b || g->pad_l != g->pad_r) return false;
-  if (g->C < 1 || g->C > NB_MAXC || g->K < 4 || g->K > NB_MAXC || (g->K & 3)) return false;
+  if (g->C < 1 || g->C > 512 || g->K < 1 || g->K > NB_MAXC) return false;
+  if (g->C > NB_MAXC && g->K > 8) return false;   // wide inputs only for the few-output-channel layers
   if (g->R * g->S != 9 && g->R * g->S != 16 && !(g->R == 7 && g->S == 7)) return false;
   const int PR = g->R, PC = g->S;  // smallest tile (one pixel) must fit
   return (size_t)(PR * PC * g->C + g->K + 2 * g->C + 8) * sizeof(float) <= 96 * 1024;
@@ -691,7 +704,7 @@ int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn
   if (p.TR > g->P) p.TR = g->P;
   auto smem_bytes = [&](int TR, int TQ) {
     const int PR = (TR - 1) * g->stride + g->R, PC = (TQ - 1) * g->stride + g->S;
-    return (size_t)(((PR * PC * g->C + 3) & ~3) + TR * TQ * g->K + 2 * g->C) * sizeof(float);
+    return (size_t)(((PR * PC * g->C + 3) & ~3) + TR * TQ * ((g->K + 3) / 4 * 4) + 2 * g->C) * sizeof(float);
   };
   while (p.TR > 1 && smem_bytes(p.TR, p.TQ) > 96 * 1024) p.TR = (p.TR + 1) / 2;
   while (p.TQ > 1 && smem_bytes(p.TR, p.TQ) > 96 * 1024) p.TQ = (p.TQ + 1) / 2;
@@ -703,7 +716,7 @@ int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn
   p.PC = (p.TQ - 1) * g->stride + g->S;
   p.row_mode = (g->R * g->S > 16) ? 1 : 0;
   p.reflect = g->pad_mode == B200GAN_PAD_REFLECT ? 1 : 0;
-  p.nsets = g->C * (g->K / 4) * (p.row_mode ? g->R : 1);
+  p.nsets = g->C * ((g->K + 3) / 4) * (p.row_mode ? g->R : 1);
   int spb = 256;
   if (p.nsets < 256) {  // fewer sets than threads: several threads share a set and split the pixels of a tile
     spb = 1;
