@@ -314,9 +314,12 @@ int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, flo
 int b200gan_nb_dz(int32_t N, int64_t PQ, int32_t K, const float *g, const float *a, const float *chan_scale,
                   int32_t act, float slope, const b200gan_nb_bn *out_bn, const double *sums, float *dz, float *db,
                   void *stream);
-/* dw [K][C][R][S] (OVERWRITTEN) from dz [N][P][Q][K] and x = BN_in(a_{l-1}) recomputed on the fly */
+/* dw [K][C][R][S] (OVERWRITTEN) from dz [N][P][Q][K] and x = BN_in(a_{l-1}) recomputed on the fly.  workspace:
+ * b200gan_nb_wgrad_workspace_floats() floats of per-block partial slabs (summed in a fixed order: deterministic); NULL or
+ * a size of 0: fp32 atomics into dw. */
+size_t b200gan_nb_wgrad_workspace_floats(const b200gan_conv_geom *g);
 int b200gan_nb_wgrad(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
-                     void *stream);
+                     float *workspace, void *stream);
 /* g_out [N][H][W][C] = gradient w.r.t. the conv's (virtual) input; packed = B200GAN_PACK_SIMT_DGRAD.  With in_bn, a_prev
  * (= the stored input a_{l-1}) and sums [2][C]: sums is OVERWRITTEN with sum g_out, sum g_out * ahat_prev, which is what
  * the backward of the BatchNorm in front of this conv needs (and its dbeta / dgamma). */

@@ -389,14 +389,18 @@ class AffineActFn(torch.autograd.Function):
 
 
 class ToChannelsLastFn(torch.autograd.Function):
+    """Layout change NCHW -> NHWC.  Linear, so under create_graph=True (gradient penalties) the
+    backward is the opposite layout node rather than a detached copy."""
+
     @staticmethod
     def forward(ctx, x):
         return ops.to_cl(x)
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        return ops.to_nchw(dy)
+        if torch.is_grad_enabled() and dy.requires_grad:
+            return ToContiguousFn.apply(dy)
+        return ops.to_nchw(dy.detach())
 
 
 class ToContiguousFn(torch.autograd.Function):
@@ -405,9 +409,10 @@ class ToContiguousFn(torch.autograd.Function):
         return ops.to_nchw(x)
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        return _as_cl(dy)
+        if torch.is_grad_enabled() and dy.requires_grad:
+            return dy if ops.is_cl(dy) else ToChannelsLastFn.apply(dy)
+        return _as_cl(dy.detach())
 
 
 class UpsampleFn(torch.autograd.Function):

@@ -420,8 +420,11 @@ def nb_dz(g_in, a, chan_scale, act, slope, out_edge, want_db):
 
 def nb_wgrad(g, x, dz, in_edge, weight_shape):
     dw = torch.empty(weight_shape, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.load().b200gan_nb_wgrad(ctypes.byref(g), _bn_ref(in_edge), x.data_ptr(), dz.data_ptr(), dw.data_ptr(),
-                                            _stream()), "nb_wgrad")
+    lib = _lib.load()
+    nws = int(lib.b200gan_nb_wgrad_workspace_floats(ctypes.byref(g)))
+    ws = torch.empty(nws, device=x.device, dtype=torch.float32) if nws else None
+    _lib.check(lib.b200gan_nb_wgrad(ctypes.byref(g), _bn_ref(in_edge), x.data_ptr(), dz.data_ptr(), dw.data_ptr(), _ptr(ws),
+                                    _stream()), "nb_wgrad")
     return dw
 
 

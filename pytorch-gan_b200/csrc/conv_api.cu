@@ -19,7 +19,8 @@ int simt_colsum(const float *x, float *out, int64_t M, int C, cudaStream_t st);
 // narrow_block.cu: shared-memory staged weight gradient of the narrow layers
 bool nb_wgrad_ok(const b200gan_conv_geom *g);
 int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
-                 cudaStream_t st);
+                 float *workspace, cudaStream_t st);
+size_t nb_wgrad_workspace_floats(const b200gan_conv_geom *g);
 // conv_tc.cu / wgrad_tc.cu
 int tc_supported(const b200gan_conv_geom *g, int pass);
 int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x,
@@ -361,9 +362,14 @@ extern "C" int b200gan_conv2d_dgrad(const b200gan_conv_geom *g, const float *dy,
   return B200GAN_OK;
 }
 
+static bool nb_wgrad_routed(const b200gan_conv_geom *g) {
+  return nb_wgrad_ok(g) && (int64_t)g->N * g->P * g->Q * g->K * g->C * g->R * g->S <= (int64_t)4e9;
+}
+
 extern "C" size_t b200gan_conv2d_wgrad_workspace_floats(const b200gan_conv_geom *g, int algo) {
   if (!g) return 0;
   if (resolve_algo(g, 2, algo) == B200GAN_ALGO_TC) return tc_wgrad_workspace_floats(g);
+  if (nb_wgrad_routed(g)) return nb_wgrad_workspace_floats(g);
   return 0;
 }
 
@@ -377,9 +383,9 @@ extern "C" int b200gan_conv2d_wgrad(const b200gan_conv_geom *g, const float *x, 
   if (a == B200GAN_ALGO_TC) {
     if (!tc_supported(g, 2)) B2_UNSUPPORTED("conv2d_wgrad: geometry not supported by the tcgen05 path");
     rc = tc_wgrad(g, x, dy, dw, workspace, st);
-  } else if (nb_wgrad_ok(g) && (int64_t)g->N * g->P * g->Q * g->K * g->C * g->R * g->S <= (int64_t)4e9) {
+  } else if (nb_wgrad_routed(g)) {
     // narrow layers (C or K small): patch + dy tile staged in shared memory, all taps of a (c, 4k) set in registers
-    rc = nb_wgrad_run(g, nullptr, x, dy, dw, st);
+    rc = nb_wgrad_run(g, nullptr, x, dy, dw, workspace, st);
   } else if (g->transposed) {
     rc = simt_wgrad(g->N, g->P, g->Q, g->K, g->H, g->W, g->C, g->R, g->S, g->stride, g->pad_t, g->pad_l,
                     B200GAN_PAD_ZERO, 1, dy, x, dw, st);

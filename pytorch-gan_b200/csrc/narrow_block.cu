@@ -203,6 +203,204 @@ nbk_fprop_kernel(const __grid_constant__ NbFprop p) {
   }
 }
 
+// ---- shared-memory staged kernels (v2) ----------------------------------------------------------------------------------
+// Copy a [rows][cols][C] window of an NHWC image into shared memory with channel pitch CP, applying v * sc + sh to
+// elements inside the image; positions outside are 0 (zero padding comes after the normalisation) or mirrored.
+// src_img == nullptr (tile hangs over the batch): all zeros.  Consecutive threads read consecutive channels: coalesced.
+__device__ __forceinline__ void nb_stage(float *dst, int CP, const float *src_img, int h0, int w0, int rows, int cols, int C,
+                                         int H, int W, const float *sc_s, const float *sh_s, bool reflect, int tid) {
+  if ((C & 3) == 0) {
+    const int C4 = C >> 2, total = rows * cols * C4;
+    for (int i = tid; i < total; i += 256) {
+      const int c4 = i % C4, pix = i / C4;
+      const int pc = pix % cols, pr = pix / cols;
+      int ih = h0 + pr, iw = w0 + pc;
+      if (reflect) {
+        ih = reflect_idx(ih, H);
+        iw = reflect_idx(iw, W);
+      }
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src_img && ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        v = __ldg(reinterpret_cast<const float4 *>(src_img + ((int64_t)ih * W + iw) * C) + c4);
+        if (sc_s) {
+          const float4 a = *reinterpret_cast<const float4 *>(sc_s + 4 * c4), b = *reinterpret_cast<const float4 *>(sh_s + 4 * c4);
+          v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+        }
+      }
+      *reinterpret_cast<float4 *>(dst + (int64_t)pix * CP + 4 * c4) = v;
+    }
+  } else {
+    const int total = rows * cols * C;
+    for (int i = tid; i < total; i += 256) {
+      const int cc = i % C, pix = i / C;
+      const int pc = pix % cols, pr = pix / cols;
+      int ih = h0 + pr, iw = w0 + pc;
+      if (reflect) {
+        ih = reflect_idx(ih, H);
+        iw = reflect_idx(iw, W);
+      }
+      float v = 0.f;
+      if (src_img && ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        v = __ldg(src_img + ((int64_t)ih * W + iw) * C + cc);
+        if (sc_s) v = fmaf(v, sc_s[cc], sh_s[cc]);
+      }
+      dst[(int64_t)pix * CP + cc] = v;
+    }
+  }
+}
+
+// tile of TP = TN images x TR x TQ pixels (powers of two, TP * KG == 256); thread = (pixel lp, group kgi of KT outputs)
+struct NbTile {
+  int TN, TR, TQ, TP, KG, KB;   // KB = KG * KT output channels per block
+  int tiles_r, tiles_q;
+};
+
+struct NbFprop2 {
+  const float *x, *wp, *bias, *cs;
+  float *y;
+  double *out_stats;
+  NbBn in_bn;
+  float *rm, *rv;
+  long long *nbt;
+  float momentum;
+  int N, H, W, C, P, Q, K, R, S, stride, pad_t, pad_l;
+  float slope;
+  int act;
+  NbTile t;
+  int PR, PC, CP;   // patch rows, columns, channel pitch (C + 4: lanes = pixels 2 * CP floats apart stay 2-way conflicted at worst)
+};
+// Forward: the patch (BatchNorm of the producer applied while staging) and this block's slice of the weights live in
+// shared memory; lanes of a warp are consecutive pixels, the KT accumulators of a thread read the weights as broadcasts.
+// dynamic smem: w [R*S*C][KB] | patch [TN][PR][PC][CP] | sc, sh [C] | red [8][2*KT]
+template <int KT>
+__global__ void __launch_bounds__(256)
+nbk_fprop2_kernel(const __grid_constant__ NbFprop2 p) {
+  extern __shared__ __align__(16) float nsm[];
+  const NbTile &t = p.t;
+  const int taps = p.R * p.S;
+  float *w_s = nsm;
+  float *x_s = w_s + (size_t)taps * p.C * t.KB;
+  float *sc_s = x_s + (((size_t)t.TN * p.PR * p.PC * p.CP + 3) & ~(size_t)3);
+  float *sh_s = sc_s + ((p.C + 3) & ~3);
+  float *red = sh_s + ((p.C + 3) & ~3);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool has_in = p.in_bn.stats != nullptr;
+  for (int cc = tid; cc < p.C; cc += 256) {
+    float mean, rstd, sc = 1.f, sh = 0.f;
+    if (has_in) {
+      nb_bn_consts(p.in_bn, p.C, cc, mean, rstd, sc, sh);
+      if (blockIdx.x == 0 && blockIdx.y == 0 && p.rm) nb_update_running(p.in_bn, p.C, cc, p.rm, p.rv, p.momentum);
+    }
+    sc_s[cc] = sc;
+    sh_s[cc] = sh;
+  }
+  if (has_in && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && p.nbt) *p.nbt += 1;
+  // this block's weights: rows (tap, c) of KB consecutive output channels
+  const int kbase = blockIdx.y * t.KB;
+  {
+    const int KB4 = t.KB >> 2, total = taps * p.C * KB4;
+    for (int i = tid; i < total; i += 256) {
+      const int col = i % KB4, row = i / KB4;
+      reinterpret_cast<float4 *>(w_s)[i] = __ldg(reinterpret_cast<const float4 *>(p.wp + (int64_t)row * p.K + kbase) + col);
+    }
+  }
+  __syncthreads();
+  int tile = blockIdx.x;
+  const int tq = tile % t.tiles_q;
+  tile /= t.tiles_q;
+  const int tr = tile % t.tiles_r;
+  const int n0 = (tile / t.tiles_r) * t.TN;
+  const int p0 = tr * t.TR, q0 = tq * t.TQ;
+  for (int li = 0; li < t.TN; ++li) {
+    const int n = n0 + li;
+    nb_stage(x_s + (size_t)li * p.PR * p.PC * p.CP, p.CP, n < p.N ? p.x + (int64_t)n * p.H * p.W * p.C : nullptr,
+             p0 * p.stride - p.pad_t, q0 * p.stride - p.pad_l, p.PR, p.PC, p.C, p.H, p.W, has_in ? sc_s : nullptr, sh_s,
+             false, tid);
+  }
+  __syncthreads();
+
+  const int lp = tid % t.TP, kgi = tid / t.TP;
+  const int lq = lp % t.TQ, lr = (lp / t.TQ) % t.TR, li = lp / (t.TQ * t.TR);
+  const int n = n0 + li, po = p0 + lr, qo = q0 + lq;
+  const bool valid = n < p.N && po < p.P && qo < p.Q;
+  float acc[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) acc[j] = 0.f;
+  const float *xb = x_s + ((size_t)(li * p.PR + lr * p.stride) * p.PC + lq * p.stride) * p.CP;
+  const float *wb = w_s + kgi * KT;
+  const int KB = t.KB;
+  for (int r = 0; r < p.R; ++r) {
+    for (int s = 0; s < p.S; ++s) {
+      const float *xt = xb + (r * p.PC + s) * p.CP;
+      const float *wt = wb + (size_t)(r * p.S + s) * p.C * KB;
+      if ((p.C & 3) == 0) {
+#pragma unroll 2
+        for (int c = 0; c < p.C; c += 4) {
+          const float4 xv = *reinterpret_cast<const float4 *>(xt + c);
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float *wr = wt + (size_t)(c + j) * KB;
+#pragma unroll
+            for (int u = 0; u < KT / 4; ++u) {
+              const float4 w4 = *reinterpret_cast<const float4 *>(wr + 4 * u);
+              acc[4 * u + 0] = fmaf(xs[j], w4.x, acc[4 * u + 0]);
+              acc[4 * u + 1] = fmaf(xs[j], w4.y, acc[4 * u + 1]);
+              acc[4 * u + 2] = fmaf(xs[j], w4.z, acc[4 * u + 2]);
+              acc[4 * u + 3] = fmaf(xs[j], w4.w, acc[4 * u + 3]);
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < p.C; ++c) {
+          const float xs = xt[c];
+          const float *wr = wt + (size_t)c * KB;
+#pragma unroll
+          for (int u = 0; u < KT / 4; ++u) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(wr + 4 * u);
+            acc[4 * u + 0] = fmaf(xs, w4.x, acc[4 * u + 0]);
+            acc[4 * u + 1] = fmaf(xs, w4.y, acc[4 * u + 1]);
+            acc[4 * u + 2] = fmaf(xs, w4.z, acc[4 * u + 2]);
+            acc[4 * u + 3] = fmaf(xs, w4.w, acc[4 * u + 3]);
+          }
+        }
+      }
+    }
+  }
+  const int k0 = kbase + kgi * KT;
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    float v = acc[j];
+    if (p.bias) v += __ldg(p.bias + k0 + j);
+    v = nb_act(v, p.act, p.slope);
+    if (p.cs && valid) v *= __ldg(p.cs + (int64_t)n * p.K + k0 + j);
+    acc[j] = valid ? v : 0.f;
+  }
+  if (valid) {
+    float *yo = p.y + ((int64_t)(n * p.P + po) * p.Q + qo) * p.K + k0;
+#pragma unroll
+    for (int u = 0; u < KT / 4; ++u)
+      *reinterpret_cast<float4 *>(yo + 4 * u) = make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+  }
+  if (p.out_stats) {
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float s1 = warp_sum(acc[j]), s2 = warp_sum(acc[j] * acc[j]);
+      if (lane == 0) {
+        red[warp * 2 * KT + j] = s1;
+        red[warp * 2 * KT + KT + j] = s2;
+      }
+    }
+    __syncthreads();
+    if (tid < t.KG * 2 * KT) {   // the TP / 32 warps of a channel group are consecutive
+      const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = t.TP >> 5;
+      float tsum = 0.f;
+      for (int wi = 0; wi < wpg; ++wi) tsum += red[(g * wpg + wi) * 2 * KT + idx];
+      atomicAdd(p.out_stats + (idx < KT ? 0 : p.K) + kbase + g * KT + (idx % KT), (double)tsum);
+    }
+  }
+}
+
 // ---- dz = BatchNorm backward (from complete sums) * Dropout2d scale * act'(a), + bias gradient ---------------------------
 struct NbDz {
   const float *g, *a, *cs;
@@ -275,6 +473,8 @@ nbk_dz_kernel(const __grid_constant__ NbDz p) {
 struct NbWgrad {
   const float *x, *dz;
   float *dw;
+  float *ws;       // per-block partial slabs [gridDim.x][dw_elems] (null: atomics straight into dw)
+  int dw_elems;
   NbBn in_bn;
   int N, H, W, C, P, Q, K, R, S, stride, pad_t, pad_l;
   int TR, TQ, tiles_r, tiles_q;  // output-pixel tile and tiles per image
@@ -293,7 +493,7 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   float *x_s = nsm;
   float *dz_s = x_s + ((p.PR * p.PC * p.C + 3) & ~3);
   float *sc_s = dz_s + p.TR * p.TQ * (((p.K + 3) >> 2) << 2);
-  float *sh_s = sc_s + p.C;
+  float *sh_s = sc_s + ((p.C + 3) & ~3);
   const int tid = threadIdx.x;
   const bool has_in = p.in_bn.stats != nullptr;
   for (int cc = tid; cc < p.C; cc += 256) {
@@ -326,20 +526,8 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
     const int p0 = tr * p.TR, q0 = tq * p.TQ;
     // patch of x_l = a_{l-1} * scale + shift (zero outside the image: the conv's zero padding comes after the norm)
     const int h0 = p0 * p.stride - p.pad_t, w0 = q0 * p.stride - p.pad_l;
-    for (int i = tid; i < p.PR * p.PC * p.C; i += 256) {
-      const int cc = i % p.C;
-      const int pc = (i / p.C) % p.PC;
-      const int pr = i / (p.C * p.PC);
-      int ih = h0 + pr, iw = w0 + pc;
-      if (p.reflect) {   // rows / columns of tiles that hang over the output edge may reflect twice: clamp afterwards
-        ih = reflect_idx(ih, p.H);
-        iw = reflect_idx(iw, p.W);
-      }
-      float v = 0.f;
-      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-        v = fmaf(__ldg(p.x + ((int64_t)(n * p.H + ih) * p.W + iw) * p.C + cc), sc_s[cc], sh_s[cc]);
-      x_s[i] = v;
-    }
+    nb_stage(x_s, p.C, p.x + (int64_t)n * p.H * p.W * p.C, h0, w0, p.PR, p.PC, p.C, p.H, p.W, has_in ? sc_s : nullptr, sh_s,
+             p.reflect != 0, tid);
     if ((p.K & 3) == 0) {
       for (int i = tid; i < tile_px * K4; i += 256) {
         const int k4 = i % K4, pix = i / K4;
@@ -377,15 +565,53 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
     }
     __syncthreads();
   }
-  // dw[k][c][r][s] (parameter layout) += this block's partial sums; pixel phases of one set hit the same addresses
-  if (set_ok) {
+  // Reduce the PS pixel phases of every set through shared memory (the tile loop ended with a barrier), then ONE value per
+  // (set, tap, k) and block goes out: a plain store into this block's slab of the workspace (summed by
+  // nbk_wgrad_reduce_kernel, deterministic), or an atomic into dw when the layer has few weights.  Same-address fp32
+  // atomics run at ~28 G/s on this part: one per thread and tap (the first version) cost 0.1 - 1.2 ms per layer.
+  constexpr int TPAD = TAPS | 1;   // odd pitch: lanes = consecutive sets write conflict-free
+  float *red = nsm;                // [PS][4][SPB][TPAD]
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (kg * 4 + j >= p.K) break;
-      float *dst = p.dw + ((int64_t)(kg * 4 + j) * p.C + c) * (p.R * p.S) + r_own * p.S;   // r_own == 0 in full mode
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int t = 0; t < TAPS; ++t) atomicAdd(dst + t, acc[t][j]);
-    }
+    for (int t = 0; t < TAPS; ++t) red[((size_t)(psplit * 4 + j) * p.SPB + set_local) * TPAD + t] = acc[t][j];
+  __syncthreads();
+  const int nout = 4 * p.SPB * TAPS;
+  const int RS = p.R * p.S;
+  float *slab = p.ws ? p.ws + (size_t)blockIdx.x * p.dw_elems : nullptr;
+  for (int o = tid; o < nout; o += 256) {
+    const int t = o % TAPS, sl = (o / TAPS) % p.SPB, j = o / (TAPS * p.SPB);
+    const int set_o = blockIdx.y * p.SPB + sl;
+    if (set_o >= p.nsets) continue;
+    const int co = set_o % p.C, kgo = (set_o / p.C) % K4;
+    const int ro = p.row_mode ? set_o / (p.C * K4) : 0;
+    const int k = kgo * 4 + j;
+    if (k >= p.K) continue;
+    float sum = 0.f;
+    for (int ps = 0; ps < p.PS; ++ps) sum += red[((size_t)(ps * 4 + j) * p.SPB + sl) * TPAD + t];
+    const int idx = (k * p.C + co) * RS + ro * p.S + t;   // dw[k][c][r][s] (parameter layout); ro == 0 in full mode
+    if (slab) slab[idx] = sum;
+    else atomicAdd(p.dw + idx, sum);
+  }
+}
+
+// dw[e] = sum over the slabs; block = 32 consecutive elements x 8 slab phases
+__global__ void __launch_bounds__(256)
+nbk_wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int elems, int nslabs) {
+  __shared__ float part[8][32];
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31), ph = threadIdx.x >> 5;
+  float a = 0.f;
+  if (e < elems) {
+#pragma unroll 4
+    for (int sl = ph; sl < nslabs; sl += 8) a += __ldg(ws + (size_t)sl * elems + e);
+  }
+  part[ph][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (ph == 0 && e < elems) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    dw[e] = t;
   }
 }
 
@@ -506,6 +732,169 @@ nbk_dgrad_kernel(const __grid_constant__ NbDgrad p) {
   }
 }
 
+struct NbDgrad2 {
+  const float *dz, *wp, *a_prev;
+  float *g_out;
+  double *sums;
+  NbBn in_bn;
+  int N, H, W, C, P, Q, K, R, S, stride, pad_t, pad_l;
+  NbTile t;         // tile of class pixels; KB = input channels (outputs of this pass) per block
+  int KP;           // channel pitch of the staged dz window (K + 4)
+  int PRm, PCm;     // window rows / columns of the class with the most taps (shared-memory carve-up)
+  int tapsm;        // most taps of a class
+};
+// Data gradient, v2: blockIdx.z = stride-parity class (all its pixels use the same Rc x Sc taps), the dz window of the
+// tile and the class's slice of the weights staged in shared memory; lanes = consecutive class pixels (consecutive dz
+// pixels: conflict-free float4 reads with pitch K + 4), the KT input channels of a thread read weights as broadcasts.
+// dynamic smem: w [tapsm*K][KB] | window [TN][PRm][PCm][KP] | mean, rstd [C] | red [8][2*KT]
+template <int KT>
+__global__ void __launch_bounds__(256)
+nbk_dgrad2_kernel(const __grid_constant__ NbDgrad2 p) {
+  extern __shared__ __align__(16) float nsm[];
+  const NbTile &t = p.t;
+  float *w_s = nsm;
+  float *d_s = w_s + (((size_t)p.tapsm * p.K * t.KB + 3) & ~(size_t)3);
+  float *mean_s = d_s + (((size_t)t.TN * p.PRm * p.PCm * p.KP + 3) & ~(size_t)3);
+  float *rstd_s = mean_s + ((p.C + 3) & ~3);
+  float *red = rstd_s + ((p.C + 3) & ~3);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool has_in = p.sums != nullptr;
+  if (has_in) {
+    for (int cc = tid; cc < p.C; cc += 256) {
+      float sc, sh;
+      nb_bn_consts(p.in_bn, p.C, cc, mean_s[cc], rstd_s[cc], sc, sh);
+    }
+  }
+  const int st = p.stride;
+  const int cls = blockIdx.z;
+  const int pa = cls / st, pb = cls % st;               // first row / column of the class
+  const int r0 = (pa + p.pad_t) % st, s0 = (pb + p.pad_l) % st;
+  const int Rc = r0 < p.R ? (p.R - r0 + st - 1) / st : 0, Sc = s0 < p.S ? (p.S - s0 + st - 1) / st : 0;
+  const int Hc = pa < p.H ? (p.H - pa + st - 1) / st : 0, Wc = pb < p.W ? (p.W - pb + st - 1) / st : 0;
+  const int oh = (pa + p.pad_t - r0) / st, ow = (pb + p.pad_l - s0) / st;   // dz row of class row i, tap ir: i + oh - ir
+  const int cbase = blockIdx.y * t.KB;
+  const int KB = t.KB;
+  // weights of the class: w_s[(ti * K + k) * KB + cc] = wp[((r * S + s) * K + k) * C + cbase + cc]
+  if ((KB & 3) == 0) {
+    const int KB4 = KB >> 2, total = Rc * Sc * p.K * KB4;
+    for (int i = tid; i < total; i += 256) {
+      const int col = i % KB4, row = i / KB4;
+      const int k = row % p.K, ti = row / p.K;
+      const int r = r0 + st * (ti / Sc), s_ = s0 + st * (ti % Sc);
+      reinterpret_cast<float4 *>(w_s)[i] =
+          __ldg(reinterpret_cast<const float4 *>(p.wp + ((int64_t)(r * p.S + s_) * p.K + k) * p.C + cbase) + col);
+    }
+  } else {
+    const int total = Rc * Sc * p.K * KB;
+    for (int i = tid; i < total; i += 256) {
+      const int col = i % KB, row = i / KB;
+      const int k = row % p.K, ti = row / p.K;
+      const int r = r0 + st * (ti / Sc), s_ = s0 + st * (ti % Sc);
+      w_s[i] = __ldg(p.wp + ((int64_t)(r * p.S + s_) * p.K + k) * p.C + cbase + col);
+    }
+  }
+  int tile = blockIdx.x;
+  const int tq = tile % t.tiles_q;
+  tile /= t.tiles_q;
+  const int tr = tile % t.tiles_r;
+  const int n0 = (tile / t.tiles_r) * t.TN;
+  const int i0 = tr * t.TR, j0 = tq * t.TQ;
+  const int PRc = t.TR + (Rc > 0 ? Rc - 1 : 0), PCc = t.TQ + (Sc > 0 ? Sc - 1 : 0);
+  for (int li = 0; li < t.TN; ++li) {
+    const int n = n0 + li;
+    nb_stage(d_s + (size_t)li * PRc * PCc * p.KP, p.KP, n < p.N ? p.dz + (int64_t)n * p.P * p.Q * p.K : nullptr,
+             i0 + oh - (Rc - 1), j0 + ow - (Sc - 1), PRc, PCc, p.K, p.P, p.Q, nullptr, nullptr, false, tid);
+  }
+  __syncthreads();
+
+  const int lp = tid % t.TP, cgi = tid / t.TP;
+  const int lq = lp % t.TQ, lr = (lp / t.TQ) % t.TR, li = lp / (t.TQ * t.TR);
+  const int n = n0 + li, ci = i0 + lr, cj = j0 + lq;
+  const bool valid = n < p.N && ci < Hc && cj < Wc;
+  float acc[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) acc[j] = 0.f;
+  const float *db = d_s + ((size_t)(li * PRc + lr) * PCc + lq) * p.KP;
+  const float *wb = w_s + cgi * KT;
+  for (int ir = 0; ir < Rc; ++ir) {
+    for (int is = 0; is < Sc; ++is) {
+      const float *dt = db + ((Rc - 1 - ir) * PCc + (Sc - 1 - is)) * p.KP;
+      const float *wt = wb + (size_t)(ir * Sc + is) * p.K * KB;
+#pragma unroll 2
+      for (int k = 0; k < p.K; k += 4) {
+        const float4 dv = *reinterpret_cast<const float4 *>(dt + k);
+        const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float *wr = wt + (size_t)(k + j) * KB;
+          if (KT % 4 == 0) {
+#pragma unroll
+            for (int u = 0; u < KT / 4; ++u) {
+              const float4 w4 = *reinterpret_cast<const float4 *>(wr + 4 * u);
+              acc[4 * u + 0] = fmaf(ds[j], w4.x, acc[4 * u + 0]);
+              acc[4 * u + 1] = fmaf(ds[j], w4.y, acc[4 * u + 1]);
+              acc[4 * u + 2] = fmaf(ds[j], w4.z, acc[4 * u + 2]);
+              acc[4 * u + 3] = fmaf(ds[j], w4.w, acc[4 * u + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < KT; ++u) acc[u] = fmaf(ds[j], wr[u], acc[u]);
+          }
+        }
+      }
+    }
+  }
+  const int c0 = cbase + cgi * KT;
+  int64_t opix = 0;
+  if (valid) {
+    opix = (int64_t)(n * p.H + pa + st * ci) * p.W + pb + st * cj;
+    float *go = p.g_out + opix * p.C + c0;
+    if (KT % 4 == 0) {
+#pragma unroll
+      for (int u = 0; u < KT / 4; ++u)
+        *reinterpret_cast<float4 *>(go + 4 * u) = make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < KT; ++j) go[j] = acc[j];
+    }
+  }
+  if (has_in) {
+    float ah[KT];
+    if (valid) {
+      if (KT % 4 == 0) {
+#pragma unroll
+        for (int u = 0; u < KT / 4; ++u) {
+          const float4 a4 = __ldg(reinterpret_cast<const float4 *>(p.a_prev + opix * p.C + c0) + u);
+          ah[4 * u] = a4.x; ah[4 * u + 1] = a4.y; ah[4 * u + 2] = a4.z; ah[4 * u + 3] = a4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) ah[j] = __ldg(p.a_prev + opix * p.C + c0 + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      float g = 0.f, gx = 0.f;
+      if (valid) {
+        g = acc[j];
+        gx = acc[j] * ((ah[j] - mean_s[c0 + j]) * rstd_s[c0 + j]);
+      }
+      const float s1 = warp_sum(g), s2 = warp_sum(gx);
+      if (lane == 0) {
+        red[warp * 2 * KT + j] = s1;
+        red[warp * 2 * KT + KT + j] = s2;
+      }
+    }
+    __syncthreads();
+    if (tid < t.KG * 2 * KT) {
+      const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = t.TP >> 5;
+      float tsum = 0.f;
+      for (int wi = 0; wi < wpg; ++wi) tsum += red[(g * wpg + wi) * 2 * KT + idx];
+      atomicAdd(p.sums + (idx < KT ? 0 : p.C) + cbase + g * KT + (idx % KT), (double)tsum);
+    }
+  }
+}
+
 // ---- tail: BatchNorm apply (+ layout) forward, layout + sums backward ----------------------------------------------------------
 struct NbTail {
   const float *a;      // [N][HW][C]
@@ -605,8 +994,80 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 using namespace b200gan;
 
+namespace b200gan {
+static int pow2ceil(int v) {
+  int r = 1;
+  while (r < v) r *= 2;
+  return r;
+}
+static bool nb_v1() {
+  static const bool v1 = getenv("B200GAN_NB_V1") && atoi(getenv("B200GAN_NB_V1")) != 0;
+  return v1;
+}
+constexpr size_t NB_SMEM_MAX = 200 * 1024;
+
+struct NbPlan {
+  NbTile t;
+  int KT;
+  size_t smem;
+  bool ok;
+};
+// Tile / channel-group choice of the staged kernels.  nout: channels this pass produces; wrow: weight floats per produced
+// channel held in shared memory; (Ho, Wo): pixel grid the tiles cover; patch(TN, TR, TQ): floats of the staged window.
+template <class F>
+static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, int nclasses, F patch) {
+  NbPlan best;
+  memset(&best, 0, sizeof(best));
+  int64_t best_score = -1;
+  int kts[2] = {0, 0};
+  if (nout % 16 == 0) { kts[0] = 16; kts[1] = 8; }
+  else if (nout % 8 == 0) kts[0] = 8;
+  else if (nout % 4 == 0) kts[0] = 4;
+  else kts[0] = 1;
+  for (int ki = 0; ki < 2 && kts[ki]; ++ki) {
+    const int KT = kts[ki];
+    for (int KG = 8; KG >= 1; KG /= 2) {
+      const int KB = KG * KT;
+      if (KB > nout || nout % KB != 0) continue;
+      NbTile t;
+      t.KG = KG; t.KB = KB; t.TP = 256 / KG;
+      t.TQ = pow2ceil(Wo) < 32 ? pow2ceil(Wo) : 32;
+      if (t.TQ > t.TP) t.TQ = t.TP;
+      t.TR = pow2ceil(Ho) < t.TP / t.TQ ? pow2ceil(Ho) : t.TP / t.TQ;
+      t.TN = t.TP / (t.TQ * t.TR);
+      t.tiles_r = ceil_div(Ho, t.TR);
+      t.tiles_q = ceil_div(Wo, t.TQ);
+      const size_t floats = (size_t)((wrow * KB + 3) & ~(int64_t)3) + ((patch(t.TN, t.TR, t.TQ) + 3) & ~(size_t)3) +
+                            2 * (size_t)((cin + 3) & ~3) + 8 * 2 * 16;
+      const size_t smem = floats * sizeof(float);
+      if (smem > NB_SMEM_MAX) continue;
+      const int64_t blocks = (int64_t)ceil_div(N, t.TN) * t.tiles_r * t.tiles_q * (nout / KB) * nclasses;
+      // fill the 148 SMs first, then prefer wide register tiles, then two resident blocks per SM
+      const int64_t score = (blocks < 148 ? blocks : 148) * 100 + KT * 10 + (smem <= 110 * 1024 ? 50 : 0);
+      if (score > best_score) {
+        best_score = score;
+        best.t = t; best.KT = KT; best.smem = smem; best.ok = true;
+      }
+    }
+  }
+  return best;
+}
+static NbPlan nb_plan_fprop(const b200gan_conv_geom *g) {
+  const int CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
+  return nb_plan(g->K, (int64_t)g->R * g->S * g->C, g->C, g->N, g->P, g->Q, 1, [&](int TN, int TR, int TQ) {
+    return (size_t)TN * ((TR - 1) * g->stride + g->R) * ((TQ - 1) * g->stride + g->S) * CP;
+  });
+}
+static NbPlan nb_plan_dgrad(const b200gan_conv_geom *g) {
+  const int st = g->stride;
+  const int Rm = ceil_div(g->R, st), Sm = ceil_div(g->S, st);
+  return nb_plan(g->C, (int64_t)Rm * Sm * g->K, g->C, g->N, ceil_div(g->H, st), ceil_div(g->W, st), st * st,
+                 [&](int TN, int TR, int TQ) { return (size_t)TN * (TR + Rm - 1) * (TQ + Sm - 1) * (g->K + 4); });
+}
+}  // namespace b200gan
+
 // geometry the fused chain takes: Conv2d, zero padding, no folded upsample, stride 1 or 2, <= 128 channels either side,
-// K a power of two >= 4 (the channel-group mappings above), fp32 SIMT.
+// K a power of two >= 4 (the channel-group mappings above), fp32 SIMT, and a tile plan that fits in shared memory.
 extern "C" int b200gan_nb_supported(const b200gan_conv_geom *g) {
   if (!g || validate_geom(g) != B200GAN_OK) return 0;
   if (g->transposed || g->up != 1 || g->pad_mode != B200GAN_PAD_ZERO) return 0;
@@ -616,6 +1077,7 @@ extern "C" int b200gan_nb_supported(const b200gan_conv_geom *g) {
   if (g->C > 1 && (g->C % 4 != 0)) return 0;
   if (g->R * g->S != 9 && g->R * g->S != 16) return 0;
   if ((int64_t)g->R * g->S * g->C * g->K * 4 > (int64_t)512 * 1024) return 0;
+  if (!nb_v1() && (!nb_plan_fprop(g).ok || !nb_plan_dgrad(g).ok)) return 0;
   return 1;
 }
 
@@ -636,7 +1098,34 @@ extern "C" int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn 
   p.rm = running_mean; p.rv = running_var; p.nbt = reinterpret_cast<long long *>(num_batches_tracked); p.momentum = momentum;
   p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
   p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l; p.slope = slope; p.act = act;
-  // more channel groups (KT = 4) when the layer has few pixels, so that the grid still fills the machine
+  if (!nb_v1()) {
+    const NbPlan pl = nb_plan_fprop(g);
+    B2_CHECK_ARG(pl.ok, "nb_fprop: no tile plan fits in shared memory");
+    NbFprop2 q;
+    q.x = x; q.wp = packed; q.bias = bias; q.cs = chan_scale; q.y = y; q.out_stats = out_stats;
+    q.in_bn = p.in_bn; q.rm = p.rm; q.rv = p.rv; q.nbt = p.nbt; q.momentum = momentum;
+    q.N = g->N; q.H = g->H; q.W = g->W; q.C = g->C; q.P = g->P; q.Q = g->Q; q.K = g->K; q.R = g->R; q.S = g->S;
+    q.stride = g->stride; q.pad_t = g->pad_t; q.pad_l = g->pad_l; q.slope = slope; q.act = act;
+    q.t = pl.t;
+    q.PR = (pl.t.TR - 1) * g->stride + g->R;
+    q.PC = (pl.t.TQ - 1) * g->stride + g->S;
+    q.CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
+    dim3 grid((unsigned)(ceil_div(g->N, pl.t.TN) * pl.t.tiles_r * pl.t.tiles_q), (unsigned)(g->K / pl.t.KB));
+    static std::atomic<uint64_t> d4{0}, d8{0}, d16{0};
+    if (pl.KT == 16) {
+      if (int e = ensure_dynamic_smem(nbk_fprop2_kernel<16>, (int)NB_SMEM_MAX, d16)) return e;
+      nbk_fprop2_kernel<16><<<grid, 256, pl.smem, st>>>(q);
+    } else if (pl.KT == 8) {
+      if (int e = ensure_dynamic_smem(nbk_fprop2_kernel<8>, (int)NB_SMEM_MAX, d8)) return e;
+      nbk_fprop2_kernel<8><<<grid, 256, pl.smem, st>>>(q);
+    } else {
+      if (int e = ensure_dynamic_smem(nbk_fprop2_kernel<4>, (int)NB_SMEM_MAX, d4)) return e;
+      nbk_fprop2_kernel<4><<<grid, 256, pl.smem, st>>>(q);
+    }
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
+  // v1 (B200GAN_NB_V1=1): direct gathers from global memory
   const int KT = (g->K % 8 == 0 && M * (g->K / 8) >= 148 * 512) ? 8 : 4;
   p.Mpad = (int)(ceil_div64(M, 256) * 256);
   const unsigned blocks = (unsigned)((int64_t)(g->K / KT) * (p.Mpad / 256));
@@ -680,70 +1169,111 @@ bool nb_wgrad_ok(const b200gan_conv_geom *g) {
   return (size_t)(PR * PC * g->C + g->K + 2 * g->C + 8) * sizeof(float) <= 96 * 1024;
 }
 int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
-                 cudaStream_t st);
+                 float *workspace, cudaStream_t st);
+size_t nb_wgrad_workspace_floats(const b200gan_conv_geom *g);
+
+struct NbWgPlan {
+  int TR, TQ, SPB, PS, nsets, nchunks, gx, row_mode;
+  size_t smem;
+  bool use_ws;
+};
+static NbWgPlan nb_wgrad_plan(const b200gan_conv_geom *g) {
+  NbWgPlan w;
+  // output tile: up to 128 pixels, whole rows when the map is narrow; the patch must fit in shared memory
+  w.TQ = g->Q < 32 ? g->Q : 32;
+  w.TR = 128 / w.TQ;
+  if (w.TR > g->P) w.TR = g->P;
+  auto smem_bytes = [&](int TR, int TQ) {
+    const int PR = (TR - 1) * g->stride + g->R, PC = (TQ - 1) * g->stride + g->S;
+    return (size_t)(((PR * PC * g->C + 3) & ~3) + TR * TQ * ((g->K + 3) / 4 * 4) + 2 * ((g->C + 3) & ~3)) * sizeof(float);
+  };
+  while (w.TR > 1 && smem_bytes(w.TR, w.TQ) > 96 * 1024) w.TR = (w.TR + 1) / 2;
+  while (w.TQ > 1 && smem_bytes(w.TR, w.TQ) > 96 * 1024) w.TQ = (w.TQ + 1) / 2;
+  w.smem = smem_bytes(w.TR, w.TQ);
+  w.row_mode = (g->R * g->S > 16) ? 1 : 0;
+  w.nsets = g->C * ((g->K + 3) / 4) * (w.row_mode ? g->R : 1);
+  int spb = 256;
+  if (w.nsets < 256) {  // fewer sets than threads: several threads share a set and split the pixels of a tile
+    spb = 1;
+    while (spb < w.nsets) spb *= 2;     // smallest power of two >= nsets (256 % spb == 0)
+  }
+  w.SPB = spb;
+  w.PS = 256 / spb;
+  w.nchunks = ceil_div(w.nsets, spb);
+  const int ntiles = g->N * ceil_div(g->P, w.TR) * ceil_div(g->Q, w.TQ);
+  w.gx = (2 * 148) / w.nchunks;
+  if (w.gx < 8) w.gx = 8;
+  if (w.gx > ntiles) w.gx = ntiles;
+  if (w.gx < 1) w.gx = 1;
+  const int taps = w.row_mode ? g->S : g->R * g->S;
+  const size_t red = (size_t)256 * 4 * (taps | 1) * sizeof(float);   // phase reduction buffer, reuses the tile memory
+  if (w.smem < red) w.smem = red;
+  // one value per weight and block: beyond ~1e5 same-address atomics per launch the slabs + reduce kernel are faster
+  w.use_ws = (int64_t)w.gx * g->K * g->C * g->R * g->S > 100000;
+  return w;
+}
+size_t nb_wgrad_workspace_floats(const b200gan_conv_geom *g) {
+  if (!nb_wgrad_ok(g) || (int64_t)g->N * g->P * g->Q == 0) return 0;
+  const NbWgPlan w = nb_wgrad_plan(g);
+  return w.use_ws ? (size_t)w.gx * g->K * g->C * g->R * g->S : 0;
+}
 }  // namespace b200gan
 
+extern "C" size_t b200gan_nb_wgrad_workspace_floats(const b200gan_conv_geom *g) {
+  if (!g || validate_geom(g) != B200GAN_OK) return 0;
+  return nb_wgrad_workspace_floats(g);
+}
+
 extern "C" int b200gan_nb_wgrad(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz,
-                                float *dw, void *stream) {
+                                float *dw, float *workspace, void *stream) {
   B2_CHECK_ARG(validate_geom(g) == B200GAN_OK && nb_wgrad_ok(g), "nb_wgrad: unsupported geometry");
   B2_CHECK_ARG(x && dz && dw, "nb_wgrad: null pointer");
-  return nb_wgrad_run(g, in_bn, x, dz, dw, as_stream(stream));
+  return nb_wgrad_run(g, in_bn, x, dz, dw, workspace, as_stream(stream));
 }
 
 int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz,
-                          float *dw, cudaStream_t st) {
-  B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)g->K * g->C * g->R * g->S * sizeof(float), st));
-  if ((int64_t)g->N * g->P * g->Q == 0) return B200GAN_OK;
+                          float *dw, float *workspace, cudaStream_t st) {
+  const int dw_elems = g->K * g->C * g->R * g->S;
+  if ((int64_t)g->N * g->P * g->Q == 0) {
+    B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)dw_elems * sizeof(float), st));
+    return B200GAN_OK;
+  }
+  const NbWgPlan w = nb_wgrad_plan(g);
+  B2_CHECK_ARG(w.smem <= 96 * 1024, "nb_wgrad: tile does not fit in shared memory");
+  const bool use_ws = w.use_ws && workspace != nullptr;
+  if (!use_ws) B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)dw_elems * sizeof(float), st));
   NbWgrad p;
-  p.x = x; p.dz = dz; p.dw = dw; p.in_bn = to_bn(in_bn);
+  p.x = x; p.dz = dz; p.dw = dw; p.ws = use_ws ? workspace : nullptr; p.dw_elems = dw_elems; p.in_bn = to_bn(in_bn);
   p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
   p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l;
-  // output tile: up to 128 pixels, whole rows when the map is narrow; the patch must fit in shared memory
-  p.TQ = g->Q < 32 ? g->Q : 32;
-  p.TR = 128 / p.TQ;
-  if (p.TR > g->P) p.TR = g->P;
-  auto smem_bytes = [&](int TR, int TQ) {
-    const int PR = (TR - 1) * g->stride + g->R, PC = (TQ - 1) * g->stride + g->S;
-    return (size_t)(((PR * PC * g->C + 3) & ~3) + TR * TQ * ((g->K + 3) / 4 * 4) + 2 * g->C) * sizeof(float);
-  };
-  while (p.TR > 1 && smem_bytes(p.TR, p.TQ) > 96 * 1024) p.TR = (p.TR + 1) / 2;
-  while (p.TQ > 1 && smem_bytes(p.TR, p.TQ) > 96 * 1024) p.TQ = (p.TQ + 1) / 2;
-  const size_t smem = smem_bytes(p.TR, p.TQ);
-  B2_CHECK_ARG(smem <= 96 * 1024, "nb_wgrad: tile does not fit in shared memory");
+  p.TR = w.TR; p.TQ = w.TQ;
   p.tiles_r = ceil_div(g->P, p.TR);
   p.tiles_q = ceil_div(g->Q, p.TQ);
   p.PR = (p.TR - 1) * g->stride + g->R;
   p.PC = (p.TQ - 1) * g->stride + g->S;
-  p.row_mode = (g->R * g->S > 16) ? 1 : 0;
+  p.row_mode = w.row_mode;
   p.reflect = g->pad_mode == B200GAN_PAD_REFLECT ? 1 : 0;
-  p.nsets = g->C * ((g->K + 3) / 4) * (p.row_mode ? g->R : 1);
-  int spb = 256;
-  if (p.nsets < 256) {  // fewer sets than threads: several threads share a set and split the pixels of a tile
-    spb = 1;
-    while (spb * 2 <= p.nsets) spb *= 2;
-    if (spb < p.nsets) spb *= 2;        // smallest power of two >= nsets (256 % spb == 0)
-  }
-  p.SPB = spb;
-  p.PS = 256 / spb;
-  const int nchunks = ceil_div(p.nsets, spb);
-  const int ntiles = g->N * p.tiles_r * p.tiles_q;
-  int gx = (2 * 148) / nchunks;
-  if (gx < 8) gx = 8;
-  if (gx > ntiles) gx = ntiles;
+  p.nsets = w.nsets;
+  p.SPB = w.SPB;
+  p.PS = w.PS;
   const int taps = g->R * g->S;
   static std::atomic<uint64_t> done9{0}, done16{0}, done7{0};
-  dim3 grid((unsigned)gx, (unsigned)nchunks);
+  dim3 grid((unsigned)w.gx, (unsigned)w.nchunks);
   if (p.row_mode) {
     if (int e = ensure_dynamic_smem(nbk_wgrad_kernel<7>, 96 * 1024, done7)) return e;
-    nbk_wgrad_kernel<7><<<grid, 256, smem, st>>>(p);
+    nbk_wgrad_kernel<7><<<grid, 256, w.smem, st>>>(p);
   } else if (taps == 9) {
     if (int e = ensure_dynamic_smem(nbk_wgrad_kernel<9>, 96 * 1024, done9)) return e;
-    nbk_wgrad_kernel<9><<<grid, 256, smem, st>>>(p);
+    nbk_wgrad_kernel<9><<<grid, 256, w.smem, st>>>(p);
   } else {
     if (int e = ensure_dynamic_smem(nbk_wgrad_kernel<16>, 96 * 1024, done16)) return e;
-    nbk_wgrad_kernel<16><<<grid, 256, smem, st>>>(p);
+    nbk_wgrad_kernel<16><<<grid, 256, w.smem, st>>>(p);
   }
   B2_LAUNCH_CHECK();
+  if (use_ws) {
+    nbk_wgrad_reduce_kernel<<<(unsigned)ceil_div(dw_elems, 32), 256, 0, st>>>(workspace, dw, dw_elems, w.gx);
+    B2_LAUNCH_CHECK();
+  }
   return B200GAN_OK;
 }
 
@@ -761,6 +1291,38 @@ extern "C" int b200gan_nb_dgrad(const b200gan_conv_geom *g, const float *dz, con
   p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
   p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l;
   const int st_ = g->stride;
+  if (!nb_v1()) {
+    const NbPlan pl = nb_plan_dgrad(g);
+    B2_CHECK_ARG(pl.ok, "nb_dgrad: no tile plan fits in shared memory");
+    NbDgrad2 q;
+    q.dz = dz; q.wp = packed; q.a_prev = a_prev; q.g_out = g_out; q.sums = sums; q.in_bn = p.in_bn;
+    q.N = g->N; q.H = g->H; q.W = g->W; q.C = g->C; q.P = g->P; q.Q = g->Q; q.K = g->K; q.R = g->R; q.S = g->S;
+    q.stride = g->stride; q.pad_t = g->pad_t; q.pad_l = g->pad_l;
+    q.t = pl.t;
+    q.KP = g->K + 4;
+    const int Rm = ceil_div(g->R, st_), Sm = ceil_div(g->S, st_);
+    q.PRm = pl.t.TR + Rm - 1;
+    q.PCm = pl.t.TQ + Sm - 1;
+    q.tapsm = Rm * Sm;
+    dim3 grid((unsigned)(ceil_div(g->N, pl.t.TN) * pl.t.tiles_r * pl.t.tiles_q), (unsigned)(g->C / pl.t.KB),
+              (unsigned)(st_ * st_));
+    static std::atomic<uint64_t> d1{0}, d4{0}, d8{0}, d16{0};
+    if (pl.KT == 16) {
+      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<16>, (int)NB_SMEM_MAX, d16)) return e;
+      nbk_dgrad2_kernel<16><<<grid, 256, pl.smem, st>>>(q);
+    } else if (pl.KT == 8) {
+      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<8>, (int)NB_SMEM_MAX, d8)) return e;
+      nbk_dgrad2_kernel<8><<<grid, 256, pl.smem, st>>>(q);
+    } else if (pl.KT == 4) {
+      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<4>, (int)NB_SMEM_MAX, d4)) return e;
+      nbk_dgrad2_kernel<4><<<grid, 256, pl.smem, st>>>(q);
+    } else {
+      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<1>, (int)NB_SMEM_MAX, d1)) return e;
+      nbk_dgrad2_kernel<1><<<grid, 256, pl.smem, st>>>(q);
+    }
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   const int64_t Mc = (int64_t)g->N * ceil_div(g->H, st_) * ceil_div(g->W, st_);  // class 0 is the largest
   p.Mpad = (int)(ceil_div64(Mc, 256) * 256);
   const int KT = g->C % 8 == 0 ? ((Mc * (g->C / 8) * st_ * st_ >= 148 * 512) ? 8 : 4) : (g->C % 4 == 0 ? 4 : 1);

@@ -66,7 +66,7 @@ def _check(ref, ours, x, seed=None, tol=1e-4, input_grad=True):
 
 
 @pytest.mark.parametrize("chans,size,n", [((1, 16, 32, 64, 128), 32, 8), ((1, 16, 32, 64, 128), 64, 128),
-                                          ((3, 8, 16), 20, 3), ((4, 16, 32, 64), 24, 5)])
+                                          ((4, 8, 16), 20, 3), ((4, 16, 32, 64), 24, 5)])
 def test_chain_without_dropout(chans, size, n):
     ref, ours = _pair(chans, p=0.0)
     _check(ref, ours, torch.randn(n, chans[0], size, size, device="cuda"))

@@ -196,7 +196,8 @@ def test_dcgan_training_steps_with_dropout_and_adam():
             step_tol = 2e-2 if b200gan.Config.algo == "simt" else max(2e-2, 1.5 * rel_err(pt - p0, pr - p0))
             assert rel_err(po - p0, pr - p0) < step_tol, (k, step_tol)
         else:
-            assert rel_err(po, pr) < 2 * TOL, k
+            # three Adam steps on TF32-level gradient noise: 2e-3, or 1.5x what stock TF32 shows on this parameter
+            assert rel_err(po, pr) < max(2 * TOL, 1.5 * rel_err(pt, pr)), k
 
 
 def test_a_script_in_the_reference_idiom_runs_under_the_launcher_on_the_gpu():

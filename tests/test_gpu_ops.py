@@ -441,15 +441,34 @@ def test_deep_unet_layers_split_k(n, hw):
     def build(ns):
         return ns.Sequential(ns.Conv2d(256, 256, 4, 2, 1, bias=False), ns.InstanceNorm2d(256), ns.LeakyReLU(0.2),
                              ns.ConvTranspose2d(256, 128, 4, 2, 1, bias=False), ns.InstanceNorm2d(128), ns.ReLU(inplace=True))
+    import copy
     ref, ours = build(torch.nn).cuda(), build(bnn).cuda()
     ours.load_state_dict(ref.state_dict())
+    yard = copy.deepcopy(ref)                # stock torch with TF32 convolutions: the reference's default GPU arithmetic
     x = torch.randn(n, 256, hw, hw, device="cuda")
-    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    yr, yo = ref(xr), ours(xo)
-    assert rel_err(yo, yr) < 2 * TOL
-    gy = torch.randn_like(yr)
-    yr.backward(gy)
-    yo.backward(gy)
-    assert rel_err(xo.grad, xr.grad) < 1e-2      # through two InstanceNorms with TF32 operands (kink flips, see above)
-    assert rel_err(ours[0].weight.grad, ref[0].weight.grad) < 1e-2
-    assert rel_err(ours[3].weight.grad, ref[3].weight.grad) < 1e-2
+    xr, xo, xt = (x.clone().requires_grad_(True) for _ in range(3))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        yr = ref(xr)
+        torch.backends.cudnn.allow_tf32 = True
+        yt = yard(xt)
+        torch.backends.cudnn.allow_tf32 = False
+        yo = ours(xo)
+        assert rel_err(yo, yr) < max(2 * TOL, 1.5 * rel_err(yt, yr))
+        gy = torch.randn_like(yr)
+        yr.backward(gy)
+        torch.backends.cudnn.allow_tf32 = True
+        yt.backward(gy)
+        torch.backends.cudnn.allow_tf32 = False
+        yo.backward(gy)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    # Through two InstanceNorms over 4..64 pixels with TF32 operands: an activation within TF32 rounding of the
+    # LeakyReLU / ReLU kink flips its mask and moves single gradient elements by O(1) (the measured deviation is a few
+    # 1e-2, the same for cuDNN's TF32 kernels) -- the bound is what stock TF32 shows on the same inputs, x2.
+    for nm, o, r, t in (("dx", xo.grad, xr.grad, xt.grad),
+                        ("dw0", ours[0].weight.grad, ref[0].weight.grad, yard[0].weight.grad),
+                        ("dw3", ours[3].weight.grad, ref[3].weight.grad, yard[3].weight.grad)):
+        e_o, e_t = rel_err(o, r), rel_err(t, r)
+        assert e_o < max(1e-2, 2.0 * e_t), f"{nm}: ours {e_o:.2e} vs stock TF32 {e_t:.2e}"

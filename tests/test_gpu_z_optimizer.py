@@ -118,12 +118,19 @@ def test_adam_step_invalidates_the_packed_weight_caches():
         oo = optim.Adam(ours.parameters(), lr=1e-2, betas=(0.5, 0.999))
         orf = torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.5, 0.999))
         x = torch.randn(2, cin, 16, 16, device="cuda")
-        for _ in range(3):
+        y_prev = None
+        for it in range(3):
             xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
             yo, yr = ours(xo), ref(xr)
-            assert rel_err(yo, yr) < 2e-3
+            # Adam's m/sqrt(v) turns TF32-level gradient noise on near-zero gradient elements into O(lr) parameter
+            # differences, so after a step the bound is 2e-2; a STALE packed copy would be off by the whole update
+            # (lr 1e-2 on weights of ~4e-2: > 1e-1), which the second assert pins down directly
+            assert rel_err(yo, yr) < (2e-3 if it == 0 else 2e-2)
+            if y_prev is not None:
+                assert rel_err(yo, y_prev) > 5e-2
+            y_prev = yo.detach().clone()
             oo.zero_grad(); orf.zero_grad()
             yo.square().mean().backward(); yr.square().mean().backward()
-            assert rel_err(xo.grad, xr.grad) < 5e-3
+            assert rel_err(xo.grad, xr.grad) < (5e-3 if it == 0 else 3e-2)
             oo.step(); orf.step()
-        assert rel_err(ours.weight, ref.weight) < 1e-3
+        assert rel_err(ours.weight, ref.weight) < 2e-2
