@@ -17,6 +17,16 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
 
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    """The oracle ops must run in true fp32 (cuDNN would otherwise pick TF32 kernels)."""
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
 # (N, C, H, K, kernel, stride, pad): the four DCGAN blocks at the BASELINE size, odd sizes, 4x4 kernels, stride 1
 GEOMS = [(128, 1, 64, 16, 3, 2, 1), (128, 16, 32, 32, 3, 2, 1), (128, 32, 16, 64, 3, 2, 1), (128, 64, 8, 128, 3, 2, 1),
          (3, 4, 20, 8, 3, 2, 1), (5, 16, 13, 32, 3, 2, 1), (6, 8, 24, 16, 4, 2, 1), (2, 32, 9, 64, 3, 1, 1),

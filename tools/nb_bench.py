@@ -1,6 +1,7 @@
 """Per-kernel timing of the fused Discriminator chain (csrc/narrow_block.cu) on the four DCGAN blocks (dcgan.py:77-88) at
-the BASELINE size (batch 128, 64x64): CUDA events around 50 back-to-back launches after 5 warm-ups (operands of one layer
-fit in L2: these are the warm numbers the training step sees, the step's launch list is the cold view).
+the BASELINE size (batch 128, 64x64): 20 launches captured in a CUDA graph, CUDA events around 10 replays (operands of one
+layer fit in L2: these are the warm numbers the training step sees; the step's ncu launch list is the cold view).  Each
+launch includes the wrapper's memset nodes (statistics / sums buffers).
     python tools/nb_bench.py            # run on the GPU box
 """
 import os
@@ -16,17 +17,30 @@ LAYERS = [("conv1 1->16 @64", 128, 1, 64, 16), ("conv2 16->32 @32", 128, 16, 32,
           ("conv4 64->128 @8", 128, 64, 8, 128)]
 
 
-def timed(fn, iters=50, warm=5):
+def timed(fn, iters=20, reps=10, warm=3):
+    """GPU time per launch: `iters` launches captured in one CUDA graph (no host launch gaps), replayed `reps` times."""
     for _ in range(warm):
         fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        fn()
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    graph.replay()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     a.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(reps):
+        graph.replay()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) * 1e3 / iters
+    return a.elapsed_time(b) * 1e3 / (iters * reps)
 
 
 def main():

@@ -45,6 +45,18 @@ def main(path):
         for h in sorted(vals):
             v, u = vals[h]
             print(f"  {h:75s} {v:>18s} {u}")
+        # where the warps wait: the six largest "stalled per issue" reasons, and shared-memory bank conflicts
+        stalls = []
+        for h, u, v in zip(hdr, units, r):
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                try:
+                    stalls.append((float(v.replace(",", "")), h))
+                except ValueError:
+                    pass
+            if "bank_conflict" in h and h.endswith(".sum"):
+                print(f"  {h:75s} {v:>18s} {u}")
+        for val, h in sorted(stalls, reverse=True)[:6]:
+            print(f"  stall {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):40s} {val:8.2f} warps per issue-active cycle")
         try:
             dur_ns = float(vals["gpu__time_duration.sum"][0].replace(",", ""))
             unit = vals["gpu__time_duration.sum"][1]
