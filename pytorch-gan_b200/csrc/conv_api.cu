@@ -21,6 +21,13 @@ bool nb_wgrad_ok(const b200gan_conv_geom *g);
 int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
                  float *workspace, cudaStream_t st);
 size_t nb_wgrad_workspace_floats(const b200gan_conv_geom *g);
+// fewk.cu: stride-1 convs with K <= 4 output channels (lanes = input channels)
+bool fewk_ok(const b200gan_conv_geom *g, int pas);
+int fewk_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
+               cudaStream_t st);
+int fewk_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, float *dx, cudaStream_t st);
+int fewk_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float *dw, float *workspace, cudaStream_t st);
+size_t fewk_wgrad_workspace_floats(const b200gan_conv_geom *g);
 // conv_tc.cu / wgrad_tc.cu
 int tc_supported(const b200gan_conv_geom *g, int pass);
 int tc_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x,
@@ -298,8 +305,15 @@ extern "C" int b200gan_conv2d_fprop(const b200gan_conv_geom *g, const b200gan_ep
     if (!tc_supported(g, 0)) B2_UNSUPPORTED("conv2d_fprop: geometry not supported by the tcgen05 path");
     return tc_fprop(g, ep, x, packed, y, st);
   }
-  int rc = simt_gather_gemm(g->N, g->H, g->W, g->C, g->P, g->Q, g->K, g->R, g->S, g->stride, g->pad_t, g->pad_l,
-                            g->pad_mode, g->up, g->transposed ? 1 : 0, ep, x, packed, y, st);
+  int rc;
+  if (fewk_ok(g, 0) && !(ep && (ep->chan_scale || ep->round_tf32))) {
+    b200gan_epilogue e2;
+    if (ep) { e2 = *ep; e2.stats = nullptr; }
+    rc = fewk_fprop(g, ep ? &e2 : nullptr, x, packed, y, st);
+  } else {
+    rc = simt_gather_gemm(g->N, g->H, g->W, g->C, g->P, g->Q, g->K, g->R, g->S, g->stride, g->pad_t, g->pad_l,
+                          g->pad_mode, g->up, g->transposed ? 1 : 0, ep, x, packed, y, st);
+  }
   if (rc) return rc;
   if (ep && ep->stats) {
     b200gan_norm_desc nd;
@@ -313,6 +327,7 @@ extern "C" int b200gan_conv2d_fprop(const b200gan_conv_geom *g, const b200gan_ep
 extern "C" size_t b200gan_conv2d_dgrad_workspace_floats(const b200gan_conv_geom *g, int algo) {
   if (!g || g->transposed) return 0;
   if (resolve_algo(g, 1, algo) == B200GAN_ALGO_TC) return 0;
+  if (fewk_ok(g, 1)) return 0;
   size_t n = 0;
   int Hv = g->H * g->up, Wv = g->W * g->up;
   if (g->pad_mode == B200GAN_PAD_REFLECT)
@@ -336,6 +351,7 @@ extern "C" int b200gan_conv2d_dgrad(const b200gan_conv_geom *g, const float *dy,
     return simt_gather_gemm(g->N, g->P, g->Q, g->K, g->H, g->W, g->C, g->R, g->S, g->stride, g->pad_t, g->pad_l,
                             B200GAN_PAD_ZERO, 1, 0, nullptr, dy, packed, dx, st);
   }
+  if (fewk_ok(g, 1)) return fewk_dgrad(g, dy, packed, dx, st);
   int Hv = g->H * g->up, Wv = g->W * g->up;
   bool reflect = g->pad_mode == B200GAN_PAD_REFLECT;
   B2_CHECK_ARG(!(reflect || g->up == 2) || workspace, "conv2d_dgrad: workspace required for reflect / upsample");
@@ -369,6 +385,7 @@ static bool nb_wgrad_routed(const b200gan_conv_geom *g) {
 extern "C" size_t b200gan_conv2d_wgrad_workspace_floats(const b200gan_conv_geom *g, int algo) {
   if (!g) return 0;
   if (resolve_algo(g, 2, algo) == B200GAN_ALGO_TC) return tc_wgrad_workspace_floats(g);
+  if (fewk_ok(g, 2)) return fewk_wgrad_workspace_floats(g);
   if (nb_wgrad_routed(g)) return nb_wgrad_workspace_floats(g);
   return 0;
 }
@@ -383,6 +400,9 @@ extern "C" int b200gan_conv2d_wgrad(const b200gan_conv_geom *g, const float *x, 
   if (a == B200GAN_ALGO_TC) {
     if (!tc_supported(g, 2)) B2_UNSUPPORTED("conv2d_wgrad: geometry not supported by the tcgen05 path");
     rc = tc_wgrad(g, x, dy, dw, workspace, st);
+  } else if (fewk_ok(g, 2)) {
+    // K <= 4 output channels, stride 1 (the image / patch output layers): lanes = input channels
+    rc = fewk_wgrad(g, x, dy, dw, workspace, st);
   } else if (nb_wgrad_routed(g)) {
     // narrow layers (C or K small): patch + dy tile staged in shared memory, all taps of a (c, 4k) set in registers
     rc = nb_wgrad_run(g, nullptr, x, dy, dw, workspace, st);

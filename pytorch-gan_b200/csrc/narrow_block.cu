@@ -1171,6 +1171,7 @@ bool nb_wgrad_ok(const b200gan_conv_geom *g) {
 int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
                  float *workspace, cudaStream_t st);
 size_t nb_wgrad_workspace_floats(const b200gan_conv_geom *g);
+int nb_wgrad_reduce(const float *ws, float *dw, int elems, int nslabs, cudaStream_t st);
 
 struct NbWgPlan {
   int TR, TQ, SPB, PS, nsets, nchunks, gx, row_mode;
@@ -1270,10 +1271,13 @@ int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn
     nbk_wgrad_kernel<16><<<grid, 256, w.smem, st>>>(p);
   }
   B2_LAUNCH_CHECK();
-  if (use_ws) {
-    nbk_wgrad_reduce_kernel<<<(unsigned)ceil_div(dw_elems, 32), 256, 0, st>>>(workspace, dw, dw_elems, w.gx);
-    B2_LAUNCH_CHECK();
-  }
+  if (use_ws) return nb_wgrad_reduce(workspace, dw, dw_elems, w.gx, st);
+  return B200GAN_OK;
+}
+
+int b200gan::nb_wgrad_reduce(const float *ws, float *dw, int elems, int nslabs, cudaStream_t st) {
+  nbk_wgrad_reduce_kernel<<<(unsigned)ceil_div(elems, 32), 256, 0, st>>>(ws, dw, elems, nslabs);
+  B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
 
