@@ -21,6 +21,12 @@ bool nb_wgrad_ok(const b200gan_conv_geom *g);
 int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
                  float *workspace, cudaStream_t st);
 size_t nb_wgrad_workspace_floats(const b200gan_conv_geom *g);
+// narrow_block.cu: the staged SIMT kernels on their own, for layers with <= 8 input channels
+bool nb_plain_fprop_ok(const b200gan_conv_geom *g);
+int nb_plain_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
+                   cudaStream_t st);
+bool nb_plain_dgrad_ok(const b200gan_conv_geom *g);
+int nb_plain_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, float *dx, cudaStream_t st);
 // fewk.cu: stride-1 convs with K <= 4 output channels (lanes = input channels)
 bool fewk_ok(const b200gan_conv_geom *g, int pas);
 int fewk_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
@@ -310,6 +316,8 @@ extern "C" int b200gan_conv2d_fprop(const b200gan_conv_geom *g, const b200gan_ep
     b200gan_epilogue e2;
     if (ep) { e2 = *ep; e2.stats = nullptr; }
     rc = fewk_fprop(g, ep ? &e2 : nullptr, x, packed, y, st);
+  } else if (nb_plain_fprop_ok(g)) {
+    rc = nb_plain_fprop(g, ep, x, packed, y, st);
   } else {
     rc = simt_gather_gemm(g->N, g->H, g->W, g->C, g->P, g->Q, g->K, g->R, g->S, g->stride, g->pad_t, g->pad_l,
                           g->pad_mode, g->up, g->transposed ? 1 : 0, ep, x, packed, y, st);
@@ -327,7 +335,7 @@ extern "C" int b200gan_conv2d_fprop(const b200gan_conv_geom *g, const b200gan_ep
 extern "C" size_t b200gan_conv2d_dgrad_workspace_floats(const b200gan_conv_geom *g, int algo) {
   if (!g || g->transposed) return 0;
   if (resolve_algo(g, 1, algo) == B200GAN_ALGO_TC) return 0;
-  if (fewk_ok(g, 1)) return 0;
+  if (fewk_ok(g, 1) || nb_plain_dgrad_ok(g)) return 0;
   size_t n = 0;
   int Hv = g->H * g->up, Wv = g->W * g->up;
   if (g->pad_mode == B200GAN_PAD_REFLECT)
@@ -352,6 +360,7 @@ extern "C" int b200gan_conv2d_dgrad(const b200gan_conv_geom *g, const float *dy,
                             B200GAN_PAD_ZERO, 1, 0, nullptr, dy, packed, dx, st);
   }
   if (fewk_ok(g, 1)) return fewk_dgrad(g, dy, packed, dx, st);
+  if (nb_plain_dgrad_ok(g)) return nb_plain_dgrad(g, dy, packed, dx, st);
   int Hv = g->H * g->up, Wv = g->W * g->up;
   bool reflect = g->pad_mode == B200GAN_PAD_REFLECT;
   B2_CHECK_ARG(!(reflect || g->up == 2) || workspace, "conv2d_dgrad: workspace required for reflect / upsample");
@@ -365,8 +374,18 @@ extern "C" int b200gan_conv2d_dgrad(const b200gan_conv_geom *g, const float *dy,
   float *dvirt = reflect ? ws_pad : (g->up == 2 ? ws_up : dx);
   int oh = reflect ? Hv + g->pad_t + g->pad_b : Hv;
   int ow = reflect ? Wv + g->pad_l + g->pad_r : Wv;
-  int rc = simt_gather_gemm(g->N, g->P, g->Q, g->K, oh, ow, g->C, g->R, g->S, g->stride, reflect ? 0 : g->pad_t,
-                            reflect ? 0 : g->pad_l, B200GAN_PAD_ZERO, 1, 1, nullptr, dy, packed, dvirt, st);
+  int rc;
+  b200gan_conv_geom gv = *g;   // the same convolution seen from the explicitly padded virtual input: no padding left
+  gv.H = oh; gv.W = ow; gv.up = 1; gv.pad_mode = B200GAN_PAD_ZERO;
+  if (reflect) gv.pad_t = gv.pad_l = gv.pad_b = gv.pad_r = 0;
+  if (reflect && g->up == 1 && fewk_ok(&gv, 1)) {
+    // few output channels (cyclegan/models.py:88-90: ReflectionPad2d(3) + Conv2d(64, 3, 7)): the channel-lane kernel
+    // writes the gradient of the padded tensor, pad2d_bwd folds the mirrored border back
+    rc = fewk_dgrad(&gv, dy, packed, dvirt, st);
+  } else {
+    rc = simt_gather_gemm(g->N, g->P, g->Q, g->K, oh, ow, g->C, g->R, g->S, g->stride, reflect ? 0 : g->pad_t,
+                          reflect ? 0 : g->pad_l, B200GAN_PAD_ZERO, 1, 1, nullptr, dy, packed, dvirt, st);
+  }
   if (rc) return rc;
   if (reflect) {
     float *dst = g->up == 2 ? ws_up : dx;

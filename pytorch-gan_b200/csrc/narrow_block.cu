@@ -66,6 +66,7 @@ __device__ __forceinline__ float nb_act_grad(float a, int act, float slope) {
   return 1.f;
 }
 
+__device__ __forceinline__ int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
 // sum over the 32 lanes of a warp
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -249,7 +250,8 @@ __device__ __forceinline__ void nb_stage(float *dst, int CP, const float *src_im
   }
 }
 
-// tile of TP = TN images x TR x TQ pixels (powers of two, TP * KG == 256); thread = (pixel lp, group kgi of KT outputs)
+// tile of TP = TN images x TR x TQ pixels (powers of two); 256 threads = (TP / PT pixel threads) x (KG channel groups),
+// a thread computes PT pixels x KT outputs
 struct NbTile {
   int TN, TR, TQ, TP, KG, KB;   // KB = KG * KT output channels per block
   int tiles_r, tiles_q;
@@ -268,11 +270,15 @@ struct NbFprop2 {
   int act;
   NbTile t;
   int PR, PC, CP;   // patch rows, columns, channel pitch (C + 4: lanes = pixels 2 * CP floats apart stay 2-way conflicted at worst)
+  int reflect;      // reflection padding (stand-alone use: cyclegan/models.py:49-50), chains are zero-padded
+  int rtf;          // store y rounded to TF32 (a tcgen05 conv consumes it next)
 };
 // Forward: the patch (BatchNorm of the producer applied while staging) and this block's slice of the weights live in
-// shared memory; lanes of a warp are consecutive pixels, the KT accumulators of a thread read the weights as broadcasts.
+// shared memory.  Thread = PT pixels x KT output channels in registers: lanes of a warp are consecutive pixels (pixel i
+// of a thread is lp + i * TPX), the weights are read as broadcasts -- one LDS.128 of weights feeds 4 * PT FMAs, one of
+// activations 4 * KT (the first version had PT = 1: 3.8 FMAs per shared-memory load, and stalled on them).
 // dynamic smem: w [R*S*C][KB] | patch [TN][PR][PC][CP] | sc, sh [C] | red [8][2*KT]
-template <int KT>
+template <int KT, int PT>
 __global__ void __launch_bounds__(256)
 nbk_fprop2_kernel(const __grid_constant__ NbFprop2 p) {
   extern __shared__ __align__(16) float nsm[];
@@ -315,85 +321,120 @@ nbk_fprop2_kernel(const __grid_constant__ NbFprop2 p) {
     const int n = n0 + li;
     nb_stage(x_s + (size_t)li * p.PR * p.PC * p.CP, p.CP, n < p.N ? p.x + (int64_t)n * p.H * p.W * p.C : nullptr,
              p0 * p.stride - p.pad_t, q0 * p.stride - p.pad_l, p.PR, p.PC, p.C, p.H, p.W, has_in ? sc_s : nullptr, sh_s,
-             false, tid);
+             p.reflect != 0, tid);
   }
   __syncthreads();
 
-  const int lp = tid % t.TP, kgi = tid / t.TP;
-  const int lq = lp % t.TQ, lr = (lp / t.TQ) % t.TR, li = lp / (t.TQ * t.TR);
-  const int n = n0 + li, po = p0 + lr, qo = q0 + lq;
-  const bool valid = n < p.N && po < p.P && qo < p.Q;
-  float acc[KT];
+  const int TPX = t.TP / PT;                 // pixel threads (a multiple of 32: a warp has one channel group)
+  const int lpx = tid % TPX, kgi = tid / TPX;
+  int xoff[PT];
+  int64_t yoff[PT];                          // < 0: pixel outside the tensor
+  int nn[PT];
 #pragma unroll
-  for (int j = 0; j < KT; ++j) acc[j] = 0.f;
-  const float *xb = x_s + ((size_t)(li * p.PR + lr * p.stride) * p.PC + lq * p.stride) * p.CP;
+  for (int i = 0; i < PT; ++i) {
+    const int lp = lpx + i * TPX;
+    const int lq = lp % t.TQ, lr = (lp / t.TQ) % t.TR, li = lp / (t.TQ * t.TR);
+    const int n = n0 + li, po = p0 + lr, qo = q0 + lq;
+    xoff[i] = ((li * p.PR + lr * p.stride) * p.PC + lq * p.stride) * p.CP;
+    nn[i] = n;
+    yoff[i] = (n < p.N && po < p.P && qo < p.Q) ? ((int64_t)(n * p.P + po) * p.Q + qo) * p.K : -1;
+  }
+  float acc[PT][KT];
+#pragma unroll
+  for (int i = 0; i < PT; ++i)
+#pragma unroll
+    for (int j = 0; j < KT; ++j) acc[i][j] = 0.f;
   const float *wb = w_s + kgi * KT;
   const int KB = t.KB;
   for (int r = 0; r < p.R; ++r) {
     for (int s = 0; s < p.S; ++s) {
-      const float *xt = xb + (r * p.PC + s) * p.CP;
+      const float *xt = x_s + (r * p.PC + s) * p.CP;
       const float *wt = wb + (size_t)(r * p.S + s) * p.C * KB;
       if ((p.C & 3) == 0) {
 #pragma unroll 2
         for (int c = 0; c < p.C; c += 4) {
-          const float4 xv = *reinterpret_cast<const float4 *>(xt + c);
-          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+          float xs[PT][4];
+#pragma unroll
+          for (int i = 0; i < PT; ++i) {
+            const float4 xv = *reinterpret_cast<const float4 *>(xt + xoff[i] + c);
+            xs[i][0] = xv.x; xs[i][1] = xv.y; xs[i][2] = xv.z; xs[i][3] = xv.w;
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float *wr = wt + (size_t)(c + j) * KB;
 #pragma unroll
             for (int u = 0; u < KT / 4; ++u) {
               const float4 w4 = *reinterpret_cast<const float4 *>(wr + 4 * u);
-              acc[4 * u + 0] = fmaf(xs[j], w4.x, acc[4 * u + 0]);
-              acc[4 * u + 1] = fmaf(xs[j], w4.y, acc[4 * u + 1]);
-              acc[4 * u + 2] = fmaf(xs[j], w4.z, acc[4 * u + 2]);
-              acc[4 * u + 3] = fmaf(xs[j], w4.w, acc[4 * u + 3]);
+#pragma unroll
+              for (int i = 0; i < PT; ++i) {
+                acc[i][4 * u + 0] = fmaf(xs[i][j], w4.x, acc[i][4 * u + 0]);
+                acc[i][4 * u + 1] = fmaf(xs[i][j], w4.y, acc[i][4 * u + 1]);
+                acc[i][4 * u + 2] = fmaf(xs[i][j], w4.z, acc[i][4 * u + 2]);
+                acc[i][4 * u + 3] = fmaf(xs[i][j], w4.w, acc[i][4 * u + 3]);
+              }
             }
           }
         }
       } else {
         for (int c = 0; c < p.C; ++c) {
-          const float xs = xt[c];
+          float xs[PT];
+#pragma unroll
+          for (int i = 0; i < PT; ++i) xs[i] = xt[xoff[i] + c];
           const float *wr = wt + (size_t)c * KB;
 #pragma unroll
           for (int u = 0; u < KT / 4; ++u) {
             const float4 w4 = *reinterpret_cast<const float4 *>(wr + 4 * u);
-            acc[4 * u + 0] = fmaf(xs, w4.x, acc[4 * u + 0]);
-            acc[4 * u + 1] = fmaf(xs, w4.y, acc[4 * u + 1]);
-            acc[4 * u + 2] = fmaf(xs, w4.z, acc[4 * u + 2]);
-            acc[4 * u + 3] = fmaf(xs, w4.w, acc[4 * u + 3]);
+#pragma unroll
+            for (int i = 0; i < PT; ++i) {
+              acc[i][4 * u + 0] = fmaf(xs[i], w4.x, acc[i][4 * u + 0]);
+              acc[i][4 * u + 1] = fmaf(xs[i], w4.y, acc[i][4 * u + 1]);
+              acc[i][4 * u + 2] = fmaf(xs[i], w4.z, acc[i][4 * u + 2]);
+              acc[i][4 * u + 3] = fmaf(xs[i], w4.w, acc[i][4 * u + 3]);
+            }
           }
         }
       }
     }
   }
   const int k0 = kbase + kgi * KT;
+  float s1[KT], s2[KT];
 #pragma unroll
-  for (int j = 0; j < KT; ++j) {
-    float v = acc[j];
-    if (p.bias) v += __ldg(p.bias + k0 + j);
-    v = nb_act(v, p.act, p.slope);
-    if (p.cs && valid) v *= __ldg(p.cs + (int64_t)n * p.K + k0 + j);
-    acc[j] = valid ? v : 0.f;
-  }
-  if (valid) {
-    float *yo = p.y + ((int64_t)(n * p.P + po) * p.Q + qo) * p.K + k0;
+  for (int j = 0; j < KT; ++j) s1[j] = s2[j] = 0.f;
 #pragma unroll
-    for (int u = 0; u < KT / 4; ++u)
-      *reinterpret_cast<float4 *>(yo + 4 * u) = make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+  for (int i = 0; i < PT; ++i) {
+    const bool valid = yoff[i] >= 0;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      float v = acc[i][j];
+      if (p.bias) v += __ldg(p.bias + k0 + j);
+      v = nb_act(v, p.act, p.slope);
+      if (p.cs && valid) v *= __ldg(p.cs + (int64_t)nn[i] * p.K + k0 + j);
+      if (p.rtf) v = round_tf32(v);
+      v = valid ? v : 0.f;
+      acc[i][j] = v;
+      s1[j] += v;
+      s2[j] = fmaf(v, v, s2[j]);
+    }
+    if (valid) {
+      float *yo = p.y + yoff[i] + k0;
+#pragma unroll
+      for (int u = 0; u < KT / 4; ++u)
+        *reinterpret_cast<float4 *>(yo + 4 * u) =
+            make_float4(acc[i][4 * u], acc[i][4 * u + 1], acc[i][4 * u + 2], acc[i][4 * u + 3]);
+    }
   }
   if (p.out_stats) {
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-      const float s1 = warp_sum(acc[j]), s2 = warp_sum(acc[j] * acc[j]);
+      const float a1 = warp_sum(s1[j]), a2 = warp_sum(s2[j]);
       if (lane == 0) {
-        red[warp * 2 * KT + j] = s1;
-        red[warp * 2 * KT + KT + j] = s2;
+        red[warp * 2 * KT + j] = a1;
+        red[warp * 2 * KT + KT + j] = a2;
       }
     }
     __syncthreads();
-    if (tid < t.KG * 2 * KT) {   // the TP / 32 warps of a channel group are consecutive
-      const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = t.TP >> 5;
+    if (tid < t.KG * 2 * KT) {   // the TPX / 32 warps of a channel group are consecutive
+      const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = TPX >> 5;
       float tsum = 0.f;
       for (int wi = 0; wi < wpg; ++wi) tsum += red[(g * wpg + wi) * 2 * KT + idx];
       atomicAdd(p.out_stats + (idx < KT ? 0 : p.K) + kbase + g * KT + (idx % KT), (double)tsum);
@@ -477,22 +518,29 @@ struct NbWgrad {
   int dw_elems;
   NbBn in_bn;
   int N, H, W, C, P, Q, K, R, S, stride, pad_t, pad_l;
-  int TR, TQ, tiles_r, tiles_q;  // output-pixel tile and tiles per image
+  int TN, TR, TQ, tiles_r, tiles_q;  // tile = TN images x TR x TQ output pixels (TN > 1 only for whole small images)
   int PR, PC;                    // patch rows / columns = (TR-1)*stride + R, (TQ-1)*stride + S
-  int SPB, PS;                   // sets per block (<= 256), pixel split = 256 / SPB
+  int SPB, PS;                   // sets per block (<= 256, a power of two), pixel split = 256 / SPB
   int nsets;                     // C * K/4 (* R in row mode)
   int row_mode;                  // 1: a set owns ONE filter row (TAPS = S): 7x7 filters (cyclegan/models.py:50)
   int reflect;                   // 1: the virtual input is reflection-padded (cyclegan/models.py:49) instead of zero-padded
 };
 // thread = set (c, kg: 4 output channels) x all TAPS taps in registers, and one of PS pixel phases.
-// grid = (persistent blocks over tiles, set chunks).  dynamic smem: patch [PR][PC][C] | dz tile [TR*TQ][K] | sc, sh [C]
+// grid = (persistent blocks over tiles, set chunks).
+// dynamic smem: patch [TN][PR][PC][C] | dz tile [TN*TR*TQ][K4*4] | sc, sh [C] | pixel offsets [TN*TR*TQ] | set bases [SPB]
 template <int TAPS>
 __global__ void __launch_bounds__(256)
 nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   extern __shared__ __align__(16) float nsm[];
-  float *x_s = nsm;
-  float *dz_s = x_s + ((p.PR * p.PC * p.C + 3) & ~3);
-  float *sc_s = dz_s + p.TR * p.TQ * (((p.K + 3) >> 2) << 2);
+  const int tile_px = p.TN * p.TR * p.TQ;
+  const int K4 = (p.K + 3) >> 2, KP = K4 * 4;   // output channels padded to a multiple of 4 inside the dz tile
+  const int patch_img = p.PR * p.PC * p.C;
+  int *sbase_s = reinterpret_cast<int *>(nsm);   // tables first: the phase reduction reuses everything behind them
+  int *sk_s = sbase_s + p.SPB;
+  int *poff_s = sk_s + p.SPB;
+  float *x_s = nsm + ((2 * p.SPB + tile_px + 3) & ~3);
+  float *dz_s = x_s + (((size_t)p.TN * patch_img + 3) & ~(size_t)3);
+  float *sc_s = dz_s + (size_t)tile_px * KP;
   float *sh_s = sc_s + ((p.C + 3) & ~3);
   const int tid = threadIdx.x;
   const bool has_in = p.in_bn.stats != nullptr;
@@ -502,10 +550,27 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
     sc_s[cc] = sc;
     sh_s[cc] = sh;
   }
-  const int set_local = tid % p.SPB, psplit = tid / p.SPB;
+  // the integer divisions happen once per block, not once per pixel / output value
+  for (int pix = tid; pix < tile_px; pix += 256) {
+    const int lq = pix % p.TQ, lr = (pix / p.TQ) % p.TR, li = pix / (p.TQ * p.TR);
+    poff_s[pix] = li * patch_img + ((lr * p.stride) * p.PC + lq * p.stride) * p.C;
+  }
+  const int RS = p.R * p.S;
+  for (int sl = tid; sl < p.SPB; sl += 256) {
+    const int set_o = blockIdx.y * p.SPB + sl;
+    int base = -1, k0 = 0;
+    if (set_o < p.nsets) {
+      const int co = set_o % p.C, kgo = (set_o / p.C) % K4;
+      const int ro = p.row_mode ? set_o / (p.C * K4) : 0;
+      k0 = kgo * 4;
+      base = (k0 * p.C + co) * RS + ro * p.S;             // dw index of (k = 4 kg, c, r, s = 0)
+    }
+    sbase_s[sl] = base;
+    sk_s[sl] = k0;
+  }
+  const int set_local = tid & (p.SPB - 1), psplit = tid / p.SPB;
   const int set = blockIdx.y * p.SPB + set_local;
   const bool set_ok = set < p.nsets;
-  const int K4 = (p.K + 3) >> 2, KP = K4 * 4;   // output channels padded to a multiple of 4 inside the dz tile
   const int c = set_ok ? set % p.C : 0, kg = set_ok ? (set / p.C) % K4 : 0;
   const int r_own = (set_ok && p.row_mode) ? set / (p.C * K4) : 0;   // filter row of this set (row mode)
   float acc[TAPS][4];
@@ -513,8 +578,7 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   for (int t = 0; t < TAPS; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
-  const int ntiles = p.N * p.tiles_r * p.tiles_q;
-  const int tile_px = p.TR * p.TQ;
+  const int ntiles = ceil_div_dev(p.N, p.TN) * p.tiles_r * p.tiles_q;
   int toff[TAPS];  // offset of tap t inside the patch, relative to the pixel's top-left element
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) toff[t] = p.row_mode ? (r_own * p.PC + t) * p.C : ((t / p.S) * p.PC + (t % p.S)) * p.C;
@@ -522,37 +586,45 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tq = tile % p.tiles_q;
     const int tr = (tile / p.tiles_q) % p.tiles_r;
-    const int n = tile / (p.tiles_q * p.tiles_r);
+    const int n0 = (tile / (p.tiles_q * p.tiles_r)) * p.TN;
     const int p0 = tr * p.TR, q0 = tq * p.TQ;
     // patch of x_l = a_{l-1} * scale + shift (zero outside the image: the conv's zero padding comes after the norm)
     const int h0 = p0 * p.stride - p.pad_t, w0 = q0 * p.stride - p.pad_l;
-    nb_stage(x_s, p.C, p.x + (int64_t)n * p.H * p.W * p.C, h0, w0, p.PR, p.PC, p.C, p.H, p.W, has_in ? sc_s : nullptr, sh_s,
-             p.reflect != 0, tid);
+    for (int li = 0; li < p.TN; ++li) {
+      const int n = n0 + li;
+      nb_stage(x_s + (size_t)li * patch_img, p.C, n < p.N ? p.x + (int64_t)n * p.H * p.W * p.C : nullptr, h0, w0, p.PR, p.PC,
+               p.C, p.H, p.W, has_in ? sc_s : nullptr, sh_s, p.reflect != 0, tid);
+    }
+    const int img_px = p.TR * p.TQ;
     if ((p.K & 3) == 0) {
       for (int i = tid; i < tile_px * K4; i += 256) {
         const int k4 = i % K4, pix = i / K4;
-        const int lr = pix / p.TQ, lq = pix % p.TQ;
+        const int li = pix / img_px, rem = pix - li * img_px;
+        const int lr = rem / p.TQ, lq = rem - lr * p.TQ;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p0 + lr < p.P && q0 + lq < p.Q)
-          v = __ldg(reinterpret_cast<const float4 *>(p.dz + ((int64_t)(n * p.P + p0 + lr) * p.Q + q0 + lq) * p.K) + k4);
+        if (n0 + li < p.N && p0 + lr < p.P && q0 + lq < p.Q)
+          v = __ldg(reinterpret_cast<const float4 *>(p.dz + ((int64_t)((n0 + li) * p.P + p0 + lr) * p.Q + q0 + lq) * p.K) + k4);
         reinterpret_cast<float4 *>(dz_s)[i] = v;
       }
     } else {
       for (int i = tid; i < tile_px * KP; i += 256) {
         const int k = i % KP, pix = i / KP;
-        const int lr = pix / p.TQ, lq = pix % p.TQ;
+        const int li = pix / img_px, rem = pix - li * img_px;
+        const int lr = rem / p.TQ, lq = rem - lr * p.TQ;
         float v = 0.f;
-        if (k < p.K && p0 + lr < p.P && q0 + lq < p.Q)
-          v = __ldg(p.dz + ((int64_t)(n * p.P + p0 + lr) * p.Q + q0 + lq) * p.K + k);
+        if (k < p.K && n0 + li < p.N && p0 + lr < p.P && q0 + lq < p.Q)
+          v = __ldg(p.dz + ((int64_t)((n0 + li) * p.P + p0 + lr) * p.Q + q0 + lq) * p.K + k);
         dz_s[i] = v;
       }
     }
     __syncthreads();
     if (set_ok) {
+      const float *xc = x_s + c;
+      const float *dk = dz_s + kg * 4;
+#pragma unroll 2
       for (int pix = psplit; pix < tile_px; pix += p.PS) {
-        const int lr = pix / p.TQ, lq = pix % p.TQ;
-        const float4 d4 = *reinterpret_cast<const float4 *>(dz_s + pix * KP + kg * 4);
-        const float *xb = x_s + ((lr * p.stride) * p.PC + lq * p.stride) * p.C + c;
+        const float4 d4 = *reinterpret_cast<const float4 *>(dk + pix * KP);
+        const float *xb = xc + poff_s[pix];
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) {
           const float xv = xb[toff[t]];
@@ -570,26 +642,24 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   // nbk_wgrad_reduce_kernel, deterministic), or an atomic into dw when the layer has few weights.  Same-address fp32
   // atomics run at ~28 G/s on this part: one per thread and tap (the first version) cost 0.1 - 1.2 ms per layer.
   constexpr int TPAD = TAPS | 1;   // odd pitch: lanes = consecutive sets write conflict-free
-  float *red = nsm;                // [PS][4][SPB][TPAD]
+  float *red = x_s;                // [PS][4][SPB][TPAD]
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) red[((size_t)(psplit * 4 + j) * p.SPB + set_local) * TPAD + t] = acc[t][j];
   __syncthreads();
   const int nout = 4 * p.SPB * TAPS;
-  const int RS = p.R * p.S;
+  const int kstride = p.C * RS;
   float *slab = p.ws ? p.ws + (size_t)blockIdx.x * p.dw_elems : nullptr;
   for (int o = tid; o < nout; o += 256) {
-    const int t = o % TAPS, sl = (o / TAPS) % p.SPB, j = o / (TAPS * p.SPB);
-    const int set_o = blockIdx.y * p.SPB + sl;
-    if (set_o >= p.nsets) continue;
-    const int co = set_o % p.C, kgo = (set_o / p.C) % K4;
-    const int ro = p.row_mode ? set_o / (p.C * K4) : 0;
-    const int k = kgo * 4 + j;
-    if (k >= p.K) continue;
+    const int t = o % TAPS, rest = o / TAPS;          // TAPS is a compile-time constant, SPB a power of two
+    const int sl = rest & (p.SPB - 1), j = rest / p.SPB;
+    const int base = sbase_s[sl];
+    if (base < 0) continue;
+    if (sk_s[sl] + j >= p.K) continue;
     float sum = 0.f;
     for (int ps = 0; ps < p.PS; ++ps) sum += red[((size_t)(ps * 4 + j) * p.SPB + sl) * TPAD + t];
-    const int idx = (k * p.C + co) * RS + ro * p.S + t;   // dw[k][c][r][s] (parameter layout); ro == 0 in full mode
+    const int idx = base + j * kstride + t;           // dw[k][c][r][s] (parameter layout)
     if (slab) slab[idx] = sum;
     else atomicAdd(p.dw + idx, sum);
   }
@@ -747,7 +817,7 @@ struct NbDgrad2 {
 // tile and the class's slice of the weights staged in shared memory; lanes = consecutive class pixels (consecutive dz
 // pixels: conflict-free float4 reads with pitch K + 4), the KT input channels of a thread read weights as broadcasts.
 // dynamic smem: w [tapsm*K][KB] | window [TN][PRm][PCm][KP] | mean, rstd [C] | red [8][2*KT]
-template <int KT>
+template <int KT, int PT>
 __global__ void __launch_bounds__(256)
 nbk_dgrad2_kernel(const __grid_constant__ NbDgrad2 p) {
   extern __shared__ __align__(16) float nsm[];
@@ -807,23 +877,36 @@ nbk_dgrad2_kernel(const __grid_constant__ NbDgrad2 p) {
   }
   __syncthreads();
 
-  const int lp = tid % t.TP, cgi = tid / t.TP;
-  const int lq = lp % t.TQ, lr = (lp / t.TQ) % t.TR, li = lp / (t.TQ * t.TR);
-  const int n = n0 + li, ci = i0 + lr, cj = j0 + lq;
-  const bool valid = n < p.N && ci < Hc && cj < Wc;
-  float acc[KT];
+  const int TPX = t.TP / PT;
+  const int lpx = tid % TPX, cgi = tid / TPX;
+  int doff[PT];
+  int64_t opix[PT];   // < 0: class pixel outside the tensor
 #pragma unroll
-  for (int j = 0; j < KT; ++j) acc[j] = 0.f;
-  const float *db = d_s + ((size_t)(li * PRc + lr) * PCc + lq) * p.KP;
+  for (int i = 0; i < PT; ++i) {
+    const int lp = lpx + i * TPX;
+    const int lq = lp % t.TQ, lr = (lp / t.TQ) % t.TR, li = lp / (t.TQ * t.TR);
+    const int n = n0 + li, ci = i0 + lr, cj = j0 + lq;
+    doff[i] = ((li * PRc + lr) * PCc + lq) * p.KP;
+    opix[i] = (n < p.N && ci < Hc && cj < Wc) ? (int64_t)(n * p.H + pa + st * ci) * p.W + pb + st * cj : -1;
+  }
+  float acc[PT][KT];
+#pragma unroll
+  for (int i = 0; i < PT; ++i)
+#pragma unroll
+    for (int j = 0; j < KT; ++j) acc[i][j] = 0.f;
   const float *wb = w_s + cgi * KT;
   for (int ir = 0; ir < Rc; ++ir) {
     for (int is = 0; is < Sc; ++is) {
-      const float *dt = db + ((Rc - 1 - ir) * PCc + (Sc - 1 - is)) * p.KP;
+      const float *dt = d_s + ((Rc - 1 - ir) * PCc + (Sc - 1 - is)) * p.KP;
       const float *wt = wb + (size_t)(ir * Sc + is) * p.K * KB;
 #pragma unroll 2
       for (int k = 0; k < p.K; k += 4) {
-        const float4 dv = *reinterpret_cast<const float4 *>(dt + k);
-        const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+        float ds[PT][4];
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+          const float4 dv = *reinterpret_cast<const float4 *>(dt + doff[i] + k);
+          ds[i][0] = dv.x; ds[i][1] = dv.y; ds[i][2] = dv.z; ds[i][3] = dv.w;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float *wr = wt + (size_t)(k + j) * KB;
@@ -831,63 +914,74 @@ nbk_dgrad2_kernel(const __grid_constant__ NbDgrad2 p) {
 #pragma unroll
             for (int u = 0; u < KT / 4; ++u) {
               const float4 w4 = *reinterpret_cast<const float4 *>(wr + 4 * u);
-              acc[4 * u + 0] = fmaf(ds[j], w4.x, acc[4 * u + 0]);
-              acc[4 * u + 1] = fmaf(ds[j], w4.y, acc[4 * u + 1]);
-              acc[4 * u + 2] = fmaf(ds[j], w4.z, acc[4 * u + 2]);
-              acc[4 * u + 3] = fmaf(ds[j], w4.w, acc[4 * u + 3]);
+#pragma unroll
+              for (int i = 0; i < PT; ++i) {
+                acc[i][4 * u + 0] = fmaf(ds[i][j], w4.x, acc[i][4 * u + 0]);
+                acc[i][4 * u + 1] = fmaf(ds[i][j], w4.y, acc[i][4 * u + 1]);
+                acc[i][4 * u + 2] = fmaf(ds[i][j], w4.z, acc[i][4 * u + 2]);
+                acc[i][4 * u + 3] = fmaf(ds[i][j], w4.w, acc[i][4 * u + 3]);
+              }
             }
           } else {
 #pragma unroll
-            for (int u = 0; u < KT; ++u) acc[u] = fmaf(ds[j], wr[u], acc[u]);
+            for (int u = 0; u < KT; ++u) {
+              const float wv = wr[u];
+#pragma unroll
+              for (int i = 0; i < PT; ++i) acc[i][u] = fmaf(ds[i][j], wv, acc[i][u]);
+            }
           }
         }
       }
     }
   }
   const int c0 = cbase + cgi * KT;
-  int64_t opix = 0;
-  if (valid) {
-    opix = (int64_t)(n * p.H + pa + st * ci) * p.W + pb + st * cj;
-    float *go = p.g_out + opix * p.C + c0;
+  float s1[KT], s2[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) s1[j] = s2[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < PT; ++i) {
+    if (opix[i] < 0) continue;
+    float *go = p.g_out + opix[i] * p.C + c0;
     if (KT % 4 == 0) {
 #pragma unroll
       for (int u = 0; u < KT / 4; ++u)
-        *reinterpret_cast<float4 *>(go + 4 * u) = make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+        *reinterpret_cast<float4 *>(go + 4 * u) =
+            make_float4(acc[i][4 * u], acc[i][4 * u + 1], acc[i][4 * u + 2], acc[i][4 * u + 3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < KT; ++j) go[j] = acc[j];
+      for (int j = 0; j < KT; ++j) go[j] = acc[i][j];
     }
-  }
-  if (has_in) {
-    float ah[KT];
-    if (valid) {
+    if (has_in) {
+      float ah[KT];
       if (KT % 4 == 0) {
 #pragma unroll
         for (int u = 0; u < KT / 4; ++u) {
-          const float4 a4 = __ldg(reinterpret_cast<const float4 *>(p.a_prev + opix * p.C + c0) + u);
+          const float4 a4 = __ldg(reinterpret_cast<const float4 *>(p.a_prev + opix[i] * p.C + c0) + u);
           ah[4 * u] = a4.x; ah[4 * u + 1] = a4.y; ah[4 * u + 2] = a4.z; ah[4 * u + 3] = a4.w;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < KT; ++j) ah[j] = __ldg(p.a_prev + opix * p.C + c0 + j);
+        for (int j = 0; j < KT; ++j) ah[j] = __ldg(p.a_prev + opix[i] * p.C + c0 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        s1[j] += acc[i][j];
+        s2[j] = fmaf(acc[i][j], (ah[j] - mean_s[c0 + j]) * rstd_s[c0 + j], s2[j]);
       }
     }
+  }
+  if (has_in) {
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-      float g = 0.f, gx = 0.f;
-      if (valid) {
-        g = acc[j];
-        gx = acc[j] * ((ah[j] - mean_s[c0 + j]) * rstd_s[c0 + j]);
-      }
-      const float s1 = warp_sum(g), s2 = warp_sum(gx);
+      const float a1 = warp_sum(s1[j]), a2 = warp_sum(s2[j]);
       if (lane == 0) {
-        red[warp * 2 * KT + j] = s1;
-        red[warp * 2 * KT + KT + j] = s2;
+        red[warp * 2 * KT + j] = a1;
+        red[warp * 2 * KT + KT + j] = a2;
       }
     }
     __syncthreads();
     if (tid < t.KG * 2 * KT) {
-      const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = t.TP >> 5;
+      const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = TPX >> 5;
       float tsum = 0.f;
       for (int wi = 0; wi < wpg; ++wi) tsum += red[(g * wpg + wi) * 2 * KT + idx];
       atomicAdd(p.sums + (idx < KT ? 0 : p.C) + cbase + g * KT + (idx % KT), (double)tsum);
@@ -1008,45 +1102,54 @@ constexpr size_t NB_SMEM_MAX = 200 * 1024;
 
 struct NbPlan {
   NbTile t;
-  int KT;
+  int KT, PT;
   size_t smem;
   bool ok;
 };
-// Tile / channel-group choice of the staged kernels.  nout: channels this pass produces; wrow: weight floats per produced
+// Tile / register-tile choice of the staged kernels.  nout: channels this pass produces; wrow: weight floats per produced
 // channel held in shared memory; (Ho, Wo): pixel grid the tiles cover; patch(TN, TR, TQ): floats of the staged window.
+// Cost model (per FMA, relative): a thread's PT x KT tile needs PT + KT shared-memory float4 loads (4 wavefronts each)
+// per 4 * PT * KT FMAs, against 4 FMA issue slots per cycle: max(1/4, (PT + KT) / (PT * KT)); divided by the SMs the
+// grid can fill.
 template <class F>
-static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, int nclasses, F patch) {
+static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, int nclasses, bool allow_pt, F patch) {
   NbPlan best;
   memset(&best, 0, sizeof(best));
-  int64_t best_score = -1;
-  int kts[2] = {0, 0};
-  if (nout % 16 == 0) { kts[0] = 16; kts[1] = 8; }
-  else if (nout % 8 == 0) kts[0] = 8;
+  double best_cost = 1e30;
+  int kts[3] = {0, 0, 0};
+  if (nout % 16 == 0) { kts[0] = 16; kts[1] = 8; kts[2] = 4; }
+  else if (nout % 8 == 0) { kts[0] = 8; kts[1] = 4; }
   else if (nout % 4 == 0) kts[0] = 4;
+  else if (nout == 3 || nout == 6) kts[0] = nout;   // image-side data gradients: all channels of a pixel in one thread
   else kts[0] = 1;
-  for (int ki = 0; ki < 2 && kts[ki]; ++ki) {
+  for (int ki = 0; ki < 3 && kts[ki]; ++ki) {
     const int KT = kts[ki];
-    for (int KG = 8; KG >= 1; KG /= 2) {
-      const int KB = KG * KT;
-      if (KB > nout || nout % KB != 0) continue;
-      NbTile t;
-      t.KG = KG; t.KB = KB; t.TP = 256 / KG;
-      t.TQ = pow2ceil(Wo) < 32 ? pow2ceil(Wo) : 32;
-      if (t.TQ > t.TP) t.TQ = t.TP;
-      t.TR = pow2ceil(Ho) < t.TP / t.TQ ? pow2ceil(Ho) : t.TP / t.TQ;
-      t.TN = t.TP / (t.TQ * t.TR);
-      t.tiles_r = ceil_div(Ho, t.TR);
-      t.tiles_q = ceil_div(Wo, t.TQ);
-      const size_t floats = (size_t)((wrow * KB + 3) & ~(int64_t)3) + ((patch(t.TN, t.TR, t.TQ) + 3) & ~(size_t)3) +
-                            2 * (size_t)((cin + 3) & ~3) + 8 * 2 * 16;
-      const size_t smem = floats * sizeof(float);
-      if (smem > NB_SMEM_MAX) continue;
-      const int64_t blocks = (int64_t)ceil_div(N, t.TN) * t.tiles_r * t.tiles_q * (nout / KB) * nclasses;
-      // fill the 148 SMs first, then prefer wide register tiles, then two resident blocks per SM
-      const int64_t score = (blocks < 148 ? blocks : 148) * 100 + KT * 10 + (smem <= 110 * 1024 ? 50 : 0);
-      if (score > best_score) {
-        best_score = score;
-        best.t = t; best.KT = KT; best.smem = smem; best.ok = true;
+    for (int PT = allow_pt ? 4 : 1; PT >= 1; PT /= 2) {
+      for (int KG = 8; KG >= 1; KG /= 2) {
+        const int KB = KG * KT;
+        if (KB > nout || nout % KB != 0) continue;
+        NbTile t;
+        t.KG = KG; t.KB = KB; t.TP = PT * (256 / KG);
+        t.TQ = pow2ceil(Wo) < 32 ? pow2ceil(Wo) : 32;
+        if (t.TQ > t.TP) t.TQ = t.TP;
+        t.TR = pow2ceil(Ho) < t.TP / t.TQ ? pow2ceil(Ho) : t.TP / t.TQ;
+        t.TN = t.TP / (t.TQ * t.TR);
+        if (t.TN > 1 && t.TN / 2 >= N) continue;           // tile mostly empty: a smaller PT / larger KG fits better
+        t.tiles_r = ceil_div(Ho, t.TR);
+        t.tiles_q = ceil_div(Wo, t.TQ);
+        const size_t floats = (size_t)((wrow * KB + 3) & ~(int64_t)3) + ((patch(t.TN, t.TR, t.TQ) + 3) & ~(size_t)3) +
+                              2 * (size_t)((cin + 3) & ~3) + 8 * 2 * 16;
+        const size_t smem = floats * sizeof(float);
+        if (smem > NB_SMEM_MAX) continue;
+        const int64_t blocks = (int64_t)ceil_div(N, t.TN) * t.tiles_r * t.tiles_q * (nout / KB) * nclasses;
+        double cost = (double)(PT + KT) / (double)(PT * KT);
+        if (cost < 0.25) cost = 0.25;
+        cost /= (double)(blocks < 148 ? blocks : 148);
+        if (smem > 110 * 1024) cost *= 1.15;                // one resident block per SM: nothing hides the staging
+        if (cost < best_cost) {
+          best_cost = cost;
+          best.t = t; best.KT = KT; best.PT = PT; best.smem = smem; best.ok = true;
+        }
       }
     }
   }
@@ -1054,14 +1157,15 @@ static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, in
 }
 static NbPlan nb_plan_fprop(const b200gan_conv_geom *g) {
   const int CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
-  return nb_plan(g->K, (int64_t)g->R * g->S * g->C, g->C, g->N, g->P, g->Q, 1, [&](int TN, int TR, int TQ) {
+  return nb_plan(g->K, (int64_t)g->R * g->S * g->C, g->C, g->N, g->P, g->Q, 1, g->R * g->S * g->C >= 16,
+                 [&](int TN, int TR, int TQ) {
     return (size_t)TN * ((TR - 1) * g->stride + g->R) * ((TQ - 1) * g->stride + g->S) * CP;
   });
 }
 static NbPlan nb_plan_dgrad(const b200gan_conv_geom *g) {
   const int st = g->stride;
   const int Rm = ceil_div(g->R, st), Sm = ceil_div(g->S, st);
-  return nb_plan(g->C, (int64_t)Rm * Sm * g->K, g->C, g->N, ceil_div(g->H, st), ceil_div(g->W, st), st * st,
+  return nb_plan(g->C, (int64_t)Rm * Sm * g->K, g->C, g->N, ceil_div(g->H, st), ceil_div(g->W, st), st * st, g->C >= 4,
                  [&](int TN, int TR, int TQ) { return (size_t)TN * (TR + Rm - 1) * (TQ + Sm - 1) * (g->K + 4); });
 }
 }  // namespace b200gan
@@ -1081,6 +1185,60 @@ extern "C" int b200gan_nb_supported(const b200gan_conv_geom *g) {
   return 1;
 }
 
+namespace b200gan {
+static int nb_fprop2_launch(const b200gan_conv_geom *g, const NbBn &in_bn, float *rm, float *rv, long long *nbt,
+                            float momentum, const float *x, const float *packed, const float *bias, int act, float slope,
+                            const float *chan_scale, float *y, double *out_stats, int reflect, int rtf, cudaStream_t st) {
+  const NbPlan pl = nb_plan_fprop(g);
+  B2_CHECK_ARG(pl.ok, "nb_fprop: no tile plan fits in shared memory");
+  NbFprop2 q;
+  q.x = x; q.wp = packed; q.bias = bias; q.cs = chan_scale; q.y = y; q.out_stats = out_stats;
+  q.in_bn = in_bn; q.rm = rm; q.rv = rv; q.nbt = nbt; q.momentum = momentum;
+  q.N = g->N; q.H = g->H; q.W = g->W; q.C = g->C; q.P = g->P; q.Q = g->Q; q.K = g->K; q.R = g->R; q.S = g->S;
+  q.stride = g->stride; q.pad_t = g->pad_t; q.pad_l = g->pad_l; q.slope = slope; q.act = act;
+  q.t = pl.t;
+  q.PR = (pl.t.TR - 1) * g->stride + g->R;
+  q.PC = (pl.t.TQ - 1) * g->stride + g->S;
+  q.CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
+  q.reflect = reflect;
+  q.rtf = rtf;
+  dim3 grid((unsigned)(ceil_div(g->N, pl.t.TN) * pl.t.tiles_r * pl.t.tiles_q), (unsigned)(g->K / pl.t.KB));
+#define NB_FPROP_CASE(KT_, PT_)                                                                              \
+  if (pl.KT == KT_ && pl.PT == PT_) {                                                                        \
+    static std::atomic<uint64_t> done{0};                                                                    \
+    if (int e = ensure_dynamic_smem(nbk_fprop2_kernel<KT_, PT_>, (int)NB_SMEM_MAX, done)) return e;          \
+    nbk_fprop2_kernel<KT_, PT_><<<grid, 256, pl.smem, st>>>(q);                                              \
+  }
+  NB_FPROP_CASE(16, 1) NB_FPROP_CASE(16, 2) NB_FPROP_CASE(16, 4)
+  NB_FPROP_CASE(8, 1) NB_FPROP_CASE(8, 2) NB_FPROP_CASE(8, 4)
+  NB_FPROP_CASE(4, 1) NB_FPROP_CASE(4, 2) NB_FPROP_CASE(4, 4)
+#undef NB_FPROP_CASE
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+// Stand-alone use of the staged forward kernel: layers with a handful of INPUT channels (the image side of every
+// network: pix2pix/models.py:76,118  Conv2d(3 | 6, 64, 4, 2, 1); cyclegan/models.py:49-50  ReflectionPad2d(3) +
+// Conv2d(3, 64, 7)), where a tensor-core tile has no K dimension to speak of.
+bool nb_plain_fprop_ok(const b200gan_conv_geom *g) {
+  if (nb_v1() || !g || g->transposed || g->up != 1) return false;
+  if (g->pad_mode != B200GAN_PAD_ZERO && g->pad_mode != B200GAN_PAD_REFLECT) return false;
+  if (g->stride != 1 && g->stride != 2) return false;
+  if (g->C < 1 || g->C > 8 || g->K < 16 || g->K > NB_MAXC || g->K % 16 != 0) return false;
+  if (g->R != g->S || (g->R != 3 && g->R != 4 && g->R != 7)) return false;
+  static const bool on = !(getenv("B200GAN_NB_PLAIN") && atoi(getenv("B200GAN_NB_PLAIN")) == 0);
+  return on && nb_plan_fprop(g).ok;
+}
+int nb_plain_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const float *x, const float *packed, float *y,
+                   cudaStream_t st) {
+  if ((int64_t)g->N * g->P * g->Q == 0) return B200GAN_OK;
+  NbBn none = to_bn(nullptr);
+  return nb_fprop2_launch(g, none, nullptr, nullptr, nullptr, 0.f, x, packed, ep ? ep->bias : nullptr,
+                          ep ? ep->act : B200GAN_ACT_NONE, ep ? ep->slope : 0.f, ep ? ep->chan_scale : nullptr, y, nullptr,
+                          g->pad_mode == B200GAN_PAD_REFLECT ? 1 : 0, ep ? ep->round_tf32 : 0, st);
+}
+}  // namespace b200gan
+
 extern "C" int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, float *running_mean,
                                 float *running_var, int64_t *num_batches_tracked, float momentum, const float *x,
                                 const float *packed, const float *bias, int32_t act, float slope, const float *chan_scale,
@@ -1098,33 +1256,9 @@ extern "C" int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn 
   p.rm = running_mean; p.rv = running_var; p.nbt = reinterpret_cast<long long *>(num_batches_tracked); p.momentum = momentum;
   p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
   p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l; p.slope = slope; p.act = act;
-  if (!nb_v1()) {
-    const NbPlan pl = nb_plan_fprop(g);
-    B2_CHECK_ARG(pl.ok, "nb_fprop: no tile plan fits in shared memory");
-    NbFprop2 q;
-    q.x = x; q.wp = packed; q.bias = bias; q.cs = chan_scale; q.y = y; q.out_stats = out_stats;
-    q.in_bn = p.in_bn; q.rm = p.rm; q.rv = p.rv; q.nbt = p.nbt; q.momentum = momentum;
-    q.N = g->N; q.H = g->H; q.W = g->W; q.C = g->C; q.P = g->P; q.Q = g->Q; q.K = g->K; q.R = g->R; q.S = g->S;
-    q.stride = g->stride; q.pad_t = g->pad_t; q.pad_l = g->pad_l; q.slope = slope; q.act = act;
-    q.t = pl.t;
-    q.PR = (pl.t.TR - 1) * g->stride + g->R;
-    q.PC = (pl.t.TQ - 1) * g->stride + g->S;
-    q.CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
-    dim3 grid((unsigned)(ceil_div(g->N, pl.t.TN) * pl.t.tiles_r * pl.t.tiles_q), (unsigned)(g->K / pl.t.KB));
-    static std::atomic<uint64_t> d4{0}, d8{0}, d16{0};
-    if (pl.KT == 16) {
-      if (int e = ensure_dynamic_smem(nbk_fprop2_kernel<16>, (int)NB_SMEM_MAX, d16)) return e;
-      nbk_fprop2_kernel<16><<<grid, 256, pl.smem, st>>>(q);
-    } else if (pl.KT == 8) {
-      if (int e = ensure_dynamic_smem(nbk_fprop2_kernel<8>, (int)NB_SMEM_MAX, d8)) return e;
-      nbk_fprop2_kernel<8><<<grid, 256, pl.smem, st>>>(q);
-    } else {
-      if (int e = ensure_dynamic_smem(nbk_fprop2_kernel<4>, (int)NB_SMEM_MAX, d4)) return e;
-      nbk_fprop2_kernel<4><<<grid, 256, pl.smem, st>>>(q);
-    }
-    B2_LAUNCH_CHECK();
-    return B200GAN_OK;
-  }
+  if (!nb_v1())
+    return nb_fprop2_launch(g, p.in_bn, p.rm, p.rv, p.nbt, momentum, x, packed, bias, act, slope, chan_scale, y, out_stats,
+                            0, 0, st);
   // v1 (B200GAN_NB_V1=1): direct gathers from global memory
   const int KT = (g->K % 8 == 0 && M * (g->K / 8) >= 148 * 512) ? 8 : 4;
   p.Mpad = (int)(ceil_div64(M, 256) * 256);
@@ -1166,7 +1300,7 @@ bool nb_wgrad_ok(const b200gan_conv_geom *g) {
   if (g->C > NB_MAXC && g->K > 8) return false;   // wide inputs only for the few-output-channel layers
   if (g->R * g->S != 9 && g->R * g->S != 16 && !(g->R == 7 && g->S == 7)) return false;
   const int PR = g->R, PC = g->S;  // smallest tile (one pixel) must fit
-  return (size_t)(PR * PC * g->C + g->K + 2 * g->C + 8) * sizeof(float) <= 96 * 1024;
+  return (size_t)(PR * PC * g->C + g->K + 2 * g->C + 8 + 2 * 256 + 8) * sizeof(float) <= 96 * 1024;
 }
 int nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, const float *x, const float *dz, float *dw,
                  float *workspace, cudaStream_t st);
@@ -1174,23 +1308,12 @@ size_t nb_wgrad_workspace_floats(const b200gan_conv_geom *g);
 int nb_wgrad_reduce(const float *ws, float *dw, int elems, int nslabs, cudaStream_t st);
 
 struct NbWgPlan {
-  int TR, TQ, SPB, PS, nsets, nchunks, gx, row_mode;
+  int TN, TR, TQ, SPB, PS, nsets, nchunks, gx, row_mode;
   size_t smem;
   bool use_ws;
 };
 static NbWgPlan nb_wgrad_plan(const b200gan_conv_geom *g) {
   NbWgPlan w;
-  // output tile: up to 128 pixels, whole rows when the map is narrow; the patch must fit in shared memory
-  w.TQ = g->Q < 32 ? g->Q : 32;
-  w.TR = 128 / w.TQ;
-  if (w.TR > g->P) w.TR = g->P;
-  auto smem_bytes = [&](int TR, int TQ) {
-    const int PR = (TR - 1) * g->stride + g->R, PC = (TQ - 1) * g->stride + g->S;
-    return (size_t)(((PR * PC * g->C + 3) & ~3) + TR * TQ * ((g->K + 3) / 4 * 4) + 2 * ((g->C + 3) & ~3)) * sizeof(float);
-  };
-  while (w.TR > 1 && smem_bytes(w.TR, w.TQ) > 96 * 1024) w.TR = (w.TR + 1) / 2;
-  while (w.TQ > 1 && smem_bytes(w.TR, w.TQ) > 96 * 1024) w.TQ = (w.TQ + 1) / 2;
-  w.smem = smem_bytes(w.TR, w.TQ);
   w.row_mode = (g->R * g->S > 16) ? 1 : 0;
   w.nsets = g->C * ((g->K + 3) / 4) * (w.row_mode ? g->R : 1);
   int spb = 256;
@@ -1201,13 +1324,35 @@ static NbWgPlan nb_wgrad_plan(const b200gan_conv_geom *g) {
   w.SPB = spb;
   w.PS = 256 / spb;
   w.nchunks = ceil_div(w.nsets, spb);
-  const int ntiles = g->N * ceil_div(g->P, w.TR) * ceil_div(g->Q, w.TQ);
+  // output tile: up to 128 pixels, whole rows when the map is narrow, several whole images when they are small; the
+  // patch must fit in shared memory
+  w.TQ = g->Q < 32 ? g->Q : 32;
+  w.TR = 128 / w.TQ;
+  if (w.TR > g->P) w.TR = g->P;
+  w.TN = 1;
+  if (w.TR == g->P && w.TQ == g->Q) {
+    w.TN = 128 / (g->P * g->Q);
+    if (w.TN > g->N) w.TN = g->N;
+    if (w.TN < 1) w.TN = 1;
+  }
+  auto tile_bytes = [&](int TN, int TR, int TQ) {
+    const int PR = (TR - 1) * g->stride + g->R, PC = (TQ - 1) * g->stride + g->S;
+    const size_t tables = (size_t)((2 * spb + TN * TR * TQ + 3) & ~3);
+    return (tables + (((size_t)TN * PR * PC * g->C + 3) & ~(size_t)3) + (size_t)TN * TR * TQ * ((g->K + 3) / 4 * 4) +
+            2 * ((g->C + 3) & ~3)) * sizeof(float);
+  };
+  while (w.TN > 1 && tile_bytes(w.TN, w.TR, w.TQ) > 96 * 1024) w.TN = (w.TN + 1) / 2;
+  while (w.TR > 1 && tile_bytes(w.TN, w.TR, w.TQ) > 96 * 1024) w.TR = (w.TR + 1) / 2;
+  while (w.TQ > 1 && tile_bytes(w.TN, w.TR, w.TQ) > 96 * 1024) w.TQ = (w.TQ + 1) / 2;
+  w.smem = tile_bytes(w.TN, w.TR, w.TQ);
+  const int ntiles = ceil_div(g->N, w.TN) * ceil_div(g->P, w.TR) * ceil_div(g->Q, w.TQ);
   w.gx = (2 * 148) / w.nchunks;
   if (w.gx < 8) w.gx = 8;
   if (w.gx > ntiles) w.gx = ntiles;
   if (w.gx < 1) w.gx = 1;
   const int taps = w.row_mode ? g->S : g->R * g->S;
-  const size_t red = (size_t)256 * 4 * (taps | 1) * sizeof(float);   // phase reduction buffer, reuses the tile memory
+  // phase reduction buffer, reuses the tile memory behind the tables
+  const size_t red = ((size_t)((2 * spb + w.TN * w.TR * w.TQ + 3) & ~3) + (size_t)256 * 4 * (taps | 1)) * sizeof(float);
   if (w.smem < red) w.smem = red;
   // one value per weight and block: beyond ~1e5 same-address atomics per launch the slabs + reduce kernel are faster
   w.use_ws = (int64_t)w.gx * g->K * g->C * g->R * g->S > 100000;
@@ -1247,7 +1392,7 @@ int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn
   p.x = x; p.dz = dz; p.dw = dw; p.ws = use_ws ? workspace : nullptr; p.dw_elems = dw_elems; p.in_bn = to_bn(in_bn);
   p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
   p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l;
-  p.TR = w.TR; p.TQ = w.TQ;
+  p.TN = w.TN; p.TR = w.TR; p.TQ = w.TQ;
   p.tiles_r = ceil_div(g->P, p.TR);
   p.tiles_q = ceil_div(g->Q, p.TQ);
   p.PR = (p.TR - 1) * g->stride + g->R;
@@ -1281,6 +1426,60 @@ int b200gan::nb_wgrad_reduce(const float *ws, float *dw, int elems, int nslabs, 
   return B200GAN_OK;
 }
 
+namespace b200gan {
+static int nb_dgrad2_launch(const b200gan_conv_geom *g, const float *dz, const float *packed, const NbBn &in_bn,
+                            const float *a_prev, float *g_out, double *sums, cudaStream_t st) {
+  const int st_ = g->stride;
+  const NbPlan pl = nb_plan_dgrad(g);
+  B2_CHECK_ARG(pl.ok, "nb_dgrad: no tile plan fits in shared memory");
+  NbDgrad2 q;
+  q.dz = dz; q.wp = packed; q.a_prev = a_prev; q.g_out = g_out; q.sums = sums; q.in_bn = in_bn;
+  q.N = g->N; q.H = g->H; q.W = g->W; q.C = g->C; q.P = g->P; q.Q = g->Q; q.K = g->K; q.R = g->R; q.S = g->S;
+  q.stride = g->stride; q.pad_t = g->pad_t; q.pad_l = g->pad_l;
+  q.t = pl.t;
+  q.KP = g->K + 4;
+  const int Rm = ceil_div(g->R, st_), Sm = ceil_div(g->S, st_);
+  q.PRm = pl.t.TR + Rm - 1;
+  q.PCm = pl.t.TQ + Sm - 1;
+  q.tapsm = Rm * Sm;
+  dim3 grid((unsigned)(ceil_div(g->N, pl.t.TN) * pl.t.tiles_r * pl.t.tiles_q), (unsigned)(g->C / pl.t.KB),
+            (unsigned)(st_ * st_));
+#define NB_DGRAD_CASE(KT_, PT_)                                                                              \
+  if (pl.KT == KT_ && pl.PT == PT_) {                                                                        \
+    static std::atomic<uint64_t> done{0};                                                                    \
+    if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<KT_, PT_>, (int)NB_SMEM_MAX, done)) return e;          \
+    nbk_dgrad2_kernel<KT_, PT_><<<grid, 256, pl.smem, st>>>(q);                                              \
+  }
+  NB_DGRAD_CASE(16, 1) NB_DGRAD_CASE(16, 2) NB_DGRAD_CASE(16, 4)
+  NB_DGRAD_CASE(8, 1) NB_DGRAD_CASE(8, 2) NB_DGRAD_CASE(8, 4)
+  NB_DGRAD_CASE(4, 1) NB_DGRAD_CASE(4, 2) NB_DGRAD_CASE(4, 4)
+  NB_DGRAD_CASE(6, 1) NB_DGRAD_CASE(6, 2) NB_DGRAD_CASE(6, 4)
+  NB_DGRAD_CASE(3, 1) NB_DGRAD_CASE(3, 2) NB_DGRAD_CASE(3, 4)
+  NB_DGRAD_CASE(1, 1)
+#undef NB_DGRAD_CASE
+  B2_LAUNCH_CHECK();
+  return B200GAN_OK;
+}
+
+// Stand-alone data gradient of a layer with a handful of INPUT channels (the discriminators' first conv, whose input
+// gradient flows back into the generator: pix2pix/models.py:118 Conv2d(6, 64, 4, 2, 1); cyclegan/models.py:116).
+bool nb_plain_dgrad_ok(const b200gan_conv_geom *g) {
+  if (nb_v1() || !g || g->transposed || g->up != 1 || g->pad_mode != B200GAN_PAD_ZERO) return false;
+  if (g->stride != 1 && g->stride != 2) return false;
+  if (g->pad_t != g->pad_b || g->pad_l != g->pad_r) return false;
+  if (g->C < 1 || g->C > 8 || (g->C != 1 && g->C != 3 && g->C != 6 && g->C % 4 != 0)) return false;
+  if (g->K < 4 || g->K > NB_MAXC || g->K % 4 != 0) return false;
+  if (g->R * g->S != 9 && g->R * g->S != 16) return false;
+  static const bool on = !(getenv("B200GAN_NB_PLAIN") && atoi(getenv("B200GAN_NB_PLAIN")) == 0);
+  return on && nb_plan_dgrad(g).ok;
+}
+int nb_plain_dgrad(const b200gan_conv_geom *g, const float *dy, const float *packed, float *dx, cudaStream_t st) {
+  if ((int64_t)g->N * g->H * g->W == 0) return B200GAN_OK;
+  NbBn none = to_bn(nullptr);
+  return nb_dgrad2_launch(g, dy, packed, none, nullptr, dx, nullptr, st);
+}
+}  // namespace b200gan
+
 extern "C" int b200gan_nb_dgrad(const b200gan_conv_geom *g, const float *dz, const float *packed,
                                 const b200gan_nb_bn *in_bn, const float *a_prev, float *g_out, double *sums,
                                 void *stream) {
@@ -1295,38 +1494,7 @@ extern "C" int b200gan_nb_dgrad(const b200gan_conv_geom *g, const float *dz, con
   p.N = g->N; p.H = g->H; p.W = g->W; p.C = g->C; p.P = g->P; p.Q = g->Q; p.K = g->K; p.R = g->R; p.S = g->S;
   p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l;
   const int st_ = g->stride;
-  if (!nb_v1()) {
-    const NbPlan pl = nb_plan_dgrad(g);
-    B2_CHECK_ARG(pl.ok, "nb_dgrad: no tile plan fits in shared memory");
-    NbDgrad2 q;
-    q.dz = dz; q.wp = packed; q.a_prev = a_prev; q.g_out = g_out; q.sums = sums; q.in_bn = p.in_bn;
-    q.N = g->N; q.H = g->H; q.W = g->W; q.C = g->C; q.P = g->P; q.Q = g->Q; q.K = g->K; q.R = g->R; q.S = g->S;
-    q.stride = g->stride; q.pad_t = g->pad_t; q.pad_l = g->pad_l;
-    q.t = pl.t;
-    q.KP = g->K + 4;
-    const int Rm = ceil_div(g->R, st_), Sm = ceil_div(g->S, st_);
-    q.PRm = pl.t.TR + Rm - 1;
-    q.PCm = pl.t.TQ + Sm - 1;
-    q.tapsm = Rm * Sm;
-    dim3 grid((unsigned)(ceil_div(g->N, pl.t.TN) * pl.t.tiles_r * pl.t.tiles_q), (unsigned)(g->C / pl.t.KB),
-              (unsigned)(st_ * st_));
-    static std::atomic<uint64_t> d1{0}, d4{0}, d8{0}, d16{0};
-    if (pl.KT == 16) {
-      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<16>, (int)NB_SMEM_MAX, d16)) return e;
-      nbk_dgrad2_kernel<16><<<grid, 256, pl.smem, st>>>(q);
-    } else if (pl.KT == 8) {
-      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<8>, (int)NB_SMEM_MAX, d8)) return e;
-      nbk_dgrad2_kernel<8><<<grid, 256, pl.smem, st>>>(q);
-    } else if (pl.KT == 4) {
-      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<4>, (int)NB_SMEM_MAX, d4)) return e;
-      nbk_dgrad2_kernel<4><<<grid, 256, pl.smem, st>>>(q);
-    } else {
-      if (int e = ensure_dynamic_smem(nbk_dgrad2_kernel<1>, (int)NB_SMEM_MAX, d1)) return e;
-      nbk_dgrad2_kernel<1><<<grid, 256, pl.smem, st>>>(q);
-    }
-    B2_LAUNCH_CHECK();
-    return B200GAN_OK;
-  }
+  if (!nb_v1()) return nb_dgrad2_launch(g, dz, packed, p.in_bn, a_prev, g_out, sums, st);
   const int64_t Mc = (int64_t)g->N * ceil_div(g->H, st_) * ceil_div(g->W, st_);  // class 0 is the largest
   p.Mpad = (int)(ceil_div64(Mc, 256) * 256);
   const int KT = g->C % 8 == 0 ? ((Mc * (g->C / 8) * st_ * st_ >= 148 * 512) ? 8 : 4) : (g->C % 4 == 0 ? 4 : 1);

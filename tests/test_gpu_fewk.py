@@ -68,3 +68,36 @@ def test_fewk_forward_and_gradients(case):
     assert rel_err(db, dz.sum((0, 2, 3))) < TOL
     dx = ops.conv_dgrad(g, dz, ops.pack_weights(g, w.detach(), PACK_SIMT_DGRAD), ALGO_SIMT)
     assert rel_err(dx, dx_ref) < TOL
+
+
+# (N, C, H, W, K, kernel, stride, pad, reflect): layers with a handful of INPUT channels -- the staged SIMT kernels of
+# csrc/narrow_block.cu on their own (nb_plain_fprop / nb_plain_dgrad)
+EDGE_CASES = [(2, 3, 32, 32, 64, 4, 2, 1, False),      # pix2pix generator down1 (models.py:76)
+              (2, 6, 32, 32, 64, 4, 2, 1, False),      # pix2pix discriminator block 1 (models.py:118)
+              (3, 6, 20, 28, 64, 4, 2, 1, False),      # ragged
+              (2, 3, 24, 24, 64, 7, 1, 3, True),       # cyclegan stem (models.py:49-50)
+              (2, 3, 16, 16, 32, 3, 2, 1, False),
+              (2, 4, 16, 16, 16, 3, 1, 1, False)]
+
+
+@pytest.mark.parametrize("case", EDGE_CASES)
+def test_few_input_channel_layers(case):
+    from b200gan import ops
+    from b200gan.functional import ACT_LRELU, ALGO_SIMT, PACK_SIMT_DGRAD, PACK_SIMT_FPROP
+    n, c, h, w_, k, ks, st, pad, reflect = case
+    torch.manual_seed(6)
+    x = torch.randn(n, c, h, w_, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(k, c, ks, ks, device="cuda") * 0.1).requires_grad_(True)
+    b = torch.randn(k, device="cuda") * 0.1
+    g, _ = ops.make_geom((n, c, h, w_), (k, c, ks, ks), st, (pad,) * 4, 1 if reflect else 0)
+    xv = F.pad(x, (pad,) * 4, mode="reflect") if reflect else x
+    z = F.conv2d(xv, w, b, st, 0 if reflect else pad)
+    y = ops.conv_fprop(g, x.detach(), ops.pack_weights(g, w.detach(), PACK_SIMT_FPROP), ALGO_SIMT, bias=b, act=ACT_LRELU,
+                       slope=0.2)
+    assert rel_err(y, F.leaky_relu(z, 0.2)) < TOL
+    dz = torch.randn_like(z).contiguous(memory_format=torch.channels_last)
+    dx_ref, dw_ref = torch.autograd.grad(z, (x, w), dz)
+    dx = ops.conv_dgrad(g, dz, ops.pack_weights(g, w.detach(), PACK_SIMT_DGRAD), ALGO_SIMT)
+    assert rel_err(dx, dx_ref) < TOL
+    dw, _ = ops.conv_wgrad(g, x.detach(), dz, tuple(w.shape), False, ALGO_SIMT)
+    assert rel_err(dw, dw_ref) < TOL
