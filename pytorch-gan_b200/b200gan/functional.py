@@ -502,11 +502,28 @@ class NbConvFn(torch.autograd.Function):
         return y
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, gy, *unused):
         x, weight, y, chan_scale = ctx.saved_tensors
         g, spec, in_edge = ctx.g, ctx.spec, ctx.in_edge
         out_edge = ctx.out_box[0] if ctx.out_box else None
+        if torch.is_grad_enabled():
+            # autograd.grad(..., create_graph=True) through a chain: the gradient penalty of a conv critic (SURVEY.md 8f
+            # N2; critics carry no BatchNorm, stargan/models.py:87-115).  Same differentiable nodes as ConvFn.
+            if in_edge is not None or out_edge is not None:
+                raise NotImplementedError("b200gan: double backward through a fused conv chain with BatchNorm2d; set "
+                                          "B200GAN_FUSE_CHAIN=0 for this model")
+            dz = gy
+            if spec.act == ACT_LRELU:
+                dz = dz * torch.where(y > 0, 1.0, spec.slope)
+            elif spec.act == ACT_RELU:
+                dz = dz * (y > 0).to(gy.dtype)
+            if chan_scale is not None:
+                dz = dz * chan_scale.view(chan_scale.shape[0], chan_scale.shape[1], 1, 1)
+            gx = ConvDgradFn.apply(dz, weight, g) if ctx.needs_input_grad[0] else None
+            dw = ConvWgradFn.apply(x, dz, g, tuple(weight.shape)) if ctx.needs_input_grad[1] else None
+            db = dz.sum((0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+            return (gx, dw, db) + (None,) * 10
+        gy, y, x = gy.detach(), y.detach(), x.detach()
         if out_edge is not None and out_edge.sums is None:
             raise RuntimeError("b200gan: fused conv chain: the consumer of this layer did not run its backward first")
         gy = _as_cl(gy)

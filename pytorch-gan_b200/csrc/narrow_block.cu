@@ -212,6 +212,7 @@ __device__ __forceinline__ void nb_stage(float *dst, int CP, const float *src_im
                                          int H, int W, const float *sc_s, const float *sh_s, bool reflect, int tid) {
   if ((C & 3) == 0) {
     const int C4 = C >> 2, total = rows * cols * C4;
+#pragma unroll 4   // independent iterations: four loads in flight per thread instead of one round trip at a time
     for (int i = tid; i < total; i += 256) {
       const int c4 = i % C4, pix = i / C4;
       const int pc = pix % cols, pr = pix / cols;
@@ -232,6 +233,7 @@ __device__ __forceinline__ void nb_stage(float *dst, int CP, const float *src_im
     }
   } else {
     const int total = rows * cols * C;
+#pragma unroll 4
     for (int i = tid; i < total; i += 256) {
       const int cc = i % C, pix = i / C;
       const int pc = pix % cols, pr = pix / cols;
@@ -305,6 +307,7 @@ nbk_fprop2_kernel(const __grid_constant__ NbFprop2 p) {
   const int kbase = blockIdx.y * t.KB;
   {
     const int KB4 = t.KB >> 2, total = taps * p.C * KB4;
+#pragma unroll 4
     for (int i = tid; i < total; i += 256) {
       const int col = i % KB4, row = i / KB4;
       reinterpret_cast<float4 *>(w_s)[i] = __ldg(reinterpret_cast<const float4 *>(p.wp + (int64_t)row * p.K + kbase) + col);
@@ -597,6 +600,7 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
     }
     const int img_px = p.TR * p.TQ;
     if ((p.K & 3) == 0) {
+#pragma unroll 4
       for (int i = tid; i < tile_px * K4; i += 256) {
         const int k4 = i % K4, pix = i / K4;
         const int li = pix / img_px, rem = pix - li * img_px;
@@ -847,6 +851,7 @@ nbk_dgrad2_kernel(const __grid_constant__ NbDgrad2 p) {
   // weights of the class: w_s[(ti * K + k) * KB + cc] = wp[((r * S + s) * K + k) * C + cbase + cc]
   if ((KB & 3) == 0) {
     const int KB4 = KB >> 2, total = Rc * Sc * p.K * KB4;
+#pragma unroll 4
     for (int i = tid; i < total; i += 256) {
       const int col = i % KB4, row = i / KB4;
       const int k = row % p.K, ti = row / p.K;
@@ -1145,7 +1150,9 @@ static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, in
         double cost = (double)(PT + KT) / (double)(PT * KT);
         if (cost < 0.25) cost = 0.25;
         cost /= (double)(blocks < 148 ? blocks : 148);
-        if (smem > 110 * 1024) cost *= 1.15;                // one resident block per SM: nothing hides the staging
+        // staging (a third of a block's life, latency-bound) only overlaps with another block's FMAs when two blocks
+        // are resident per SM and the grid is large enough to put two on every SM
+        if (smem > 110 * 1024 || blocks < 256) cost *= 1.4;
         if (cost < best_cost) {
           best_cost = cost;
           best.t = t; best.KT = KT; best.PT = PT; best.smem = smem; best.ok = true;

@@ -134,3 +134,32 @@ def test_adam_step_invalidates_the_packed_weight_caches():
             assert rel_err(xo.grad, xr.grad) < (5e-3 if it == 0 else 3e-2)
             oo.step(); orf.step()
         assert rel_err(ours.weight, ref.weight) < 2e-2
+
+
+def test_multi_pack_is_bit_identical_to_the_per_layer_pack():
+    """b200gan_pack_weights_multi (one launch per optimizer step, tiles transposed through shared memory) against
+    b200gan_pack_weights (one launch per copy): every layout, Conv2d and ConvTranspose2d parameters, ragged channel
+    counts, the folded x2-upsample layouts -- index arithmetic only, so bit-exact."""
+    from b200gan import ops
+    from b200gan import _lib
+    torch.manual_seed(11)
+    cases = []   # (x shape, weight shape, stride, pads, up, transposed, kinds)
+    plain = (_lib.PACK_SIMT_FPROP, _lib.PACK_SIMT_DGRAD, _lib.PACK_TC_FPROP, _lib.PACK_TC_DGRAD)
+    cases.append(((2, 64, 16, 16), (128, 64, 4, 4), 2, (1, 1, 1, 1), 1, False, plain))
+    cases.append(((2, 40, 16, 16), (72, 40, 3, 3), 1, (1, 1, 1, 1), 1, False, plain))        # ragged tiles
+    cases.append(((2, 128, 8, 8), (128, 64, 4, 4), 2, (1, 1, 1, 1), 1, True, plain))         # ConvTranspose2d [Cin][Cout][R][S]
+    cases.append(((2, 3, 16, 16), (64, 3, 4, 4), 2, (1, 1, 1, 1), 1, False, plain))          # too narrow for tiles
+    cases.append(((2, 128, 16, 16), (64, 128, 3, 3), 1, (1, 1, 1, 1), 2, False,
+                  (_lib.PACK_TC_FPROP_UP2, _lib.PACK_TC_DGRAD_UP2)))
+    jobs, singles = [], []
+    for xs, ws, st, pads, up, tr, kinds in cases:
+        w = torch.randn(*ws, device="cuda")
+        g, _ = ops.make_geom(xs, ws, st, pads, 0, up, tr)
+        for kind in kinds:
+            single = ops.pack_weights(g, w, kind)
+            buf = torch.full_like(single, float("nan"))
+            jobs.append((g, kind, w, buf))
+            singles.append(single)
+    ops.pack_weights_multi(jobs)
+    for (g, kind, w, buf), single in zip(jobs, singles):
+        assert torch.equal(buf, single), (tuple(w.shape), kind)
