@@ -305,6 +305,24 @@ __device__ __forceinline__ void ring_produce(const float *__restrict__ a, int64_
   }
 }
 
+// (h, w) of the pixel `off` columns after column 0 of row h0 -- 32-bit arithmetic (a shift when W is a power of two).
+// The first version took pix % W and (pix / W) % H in 64 bits for every pixel: over half of the kernels' instructions.
+__device__ __forceinline__ void tail_hw(int off, int h0, int W, int H, int wsh, int &w, int &h) {
+  int q;
+  if (wsh >= 0) { q = off >> wsh; w = off & (W - 1); }
+  else { q = (int)((unsigned)off / (unsigned)W); w = off - q * W; }
+  h = h0 + q;
+  if (h >= H) h = (int)((unsigned)h % (unsigned)H);
+}
+
+__device__ __forceinline__ void tail_advance(int &w0, int &h0, int step, int W, int H, int wsh) {
+  w0 += step;
+  const int q = wsh >= 0 ? (w0 >> wsh) : (int)((unsigned)w0 / (unsigned)W);
+  w0 -= q * W;
+  h0 += q;
+  if (h0 >= H) h0 = (int)((unsigned)h0 % (unsigned)H);
+}
+
 // the nine neighbours g[h + 1 - r][w + 1 - s] (zero outside the image) of channel k
 template <int KK>
 __device__ __forceinline__ void load_gn(const float *__restrict__ g, int64_t pix, int h, int w, int H, int W,
@@ -382,18 +400,20 @@ tail_bwd_reduce_kernel(const __grid_constant__ TailBwdP p) {
     const float slope = p.slope;
     const uint32_t wsm_a = smem_u32(wsm) + c4 * 16;
     const int64_t nchunks = (b1 - b0 + RB_CHUNK - 1) / RB_CHUNK;
+    int cw0 = (int)(b0 % W), ch0 = (int)((b0 / W) % H);   // (w, h) of the chunk\'s first pixel, advanced per chunk
+    const int wsh = (W & (W - 1)) == 0 ? 31 - __clz(W) : -1;
     for (int64_t i = 0; i < nchunks; ++i) {
       const int stage = (int)(i % RB_STAGES);
       mbar_wait(&full[stage], (uint32_t)((i / RB_STAGES) & 1));
       const int64_t px0 = b0 + i * RB_CHUNK;
       const uint32_t sbase = ring + stage * (RB_CHUNK * C * 4) + c4 * 16;
-#pragma unroll 2
+#pragma unroll 1
       for (int lp = warp * PPW + ps; lp < RB_CHUNK; lp += PPB) {
         const int64_t pix = px0 + lp;
         if (pix >= b1) break;
         const float4 av = ld_shared_v4(sbase + lp * (C * 4));
-        const int w = (int)(pix % W);
-        const int h = (int)((pix / W) % H);
+        int w, h;
+        tail_hw(cw0 + lp, ch0, W, H, wsh, w, h);
         float gn[KK][9];
         load_gn<KK>(p.g, pix, h, w, H, W, gn);
         const float x[4] = {av.x, av.y, av.z, av.w};
@@ -428,6 +448,7 @@ tail_bwd_reduce_kernel(const __grid_constant__ TailBwdP p) {
           for (int k = 0; k < KK; ++k) dba[k] += gn[k][4];  // centre tap = g at this pixel
         }
       }
+      tail_advance(cw0, ch0, RB_CHUNK, W, H, wsh);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
     }
@@ -519,6 +540,8 @@ tail_bwd_apply_kernel(const __grid_constant__ TailBwdP p) {
   const uint32_t wsm_a = smem_u32(wsm) + c4 * 16;
   float4 *da4 = reinterpret_cast<float4 *>(p.da);
   const int64_t nchunks = (b1 - b0 + RB_CHUNK - 1) / RB_CHUNK;
+  int cw0 = (int)(b0 % W), ch0 = (int)((b0 / W) % H);   // (w, h) of the chunk\'s first pixel, advanced per chunk
+  const int wsh = (W & (W - 1)) == 0 ? 31 - __clz(W) : -1;
   for (int64_t i = 0; i < nchunks; ++i) {
     const int stage = (int)(i % RB_STAGES);
     mbar_wait(&full[stage], (uint32_t)((i / RB_STAGES) & 1));
@@ -529,8 +552,8 @@ tail_bwd_apply_kernel(const __grid_constant__ TailBwdP p) {
       const int64_t pix = px0 + lp;
       if (pix >= b1) break;
       const float4 av = ld_shared_v4(sbase + lp * (C * 4));
-      const int w = (int)(pix % W);
-      const int h = (int)((pix / W) % H);
+      int w, h;
+      tail_hw(cw0 + lp, ch0, W, H, wsh, w, h);
       float gn[KK][9];
       load_gn<KK>(p.g, pix, h, w, H, W, gn);
       const float x[4] = {av.x, av.y, av.z, av.w};
@@ -557,6 +580,7 @@ tail_bwd_apply_kernel(const __grid_constant__ TailBwdP p) {
       }
       da4[pix * C4 + c4] = make_float4(o[0], o[1], o[2], o[3]);
     }
+    tail_advance(cw0, ch0, RB_CHUNK, W, H, wsh);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
   }
