@@ -509,10 +509,15 @@ def run_gpu(args):
         for g_ in groups:
             g_["share_of_step"] = g_["ms"] * g_["per_step"] / step_ms
         dom = max(groups, key=lambda g_: g_["share_of_step"])
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
+        # kernels (profiles/r2_ncu_full_tail_kernels_c3.txt; the kernels' traffic is set by the algorithm, not the timing)
+        ncu_traffic = {"G tail fprop": 145.4e6, "G tail backward": 141.6e6 + 218.7e6}
+        dom_traffic = next((v for k_, v in ncu_traffic.items() if dom["kernel"].startswith(k_)), None)
         tc = [g_ for g_ in groups if g_["bound"] == "tensor"]
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
                     "unit": dom["unit"], "frac": dom["frac"], "ms_per_launch": dom["ms"],
-                    "share_of_step": dom["share_of_step"], "traffic": None,
+                    "share_of_step": dom["share_of_step"], "traffic": dom_traffic,
+                    "traffic_source": "profiles/r2_ncu_full_tail_kernels_c3.txt (bytes per launch)" if dom_traffic else None,
                     "peak_source": peak_src + ("; TF32 = bf16/2" if dom["bound"] == "tensor" else ""),
                     "step_tensor_fraction_reference_form": cfg["gflop"] / step_ms / tf32_peak,
                     "step_gflop_reference_form": cfg["gflop"],
