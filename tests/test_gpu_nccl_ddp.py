@@ -133,7 +133,10 @@ def test_dcgan_step_on_two_ranks_equals_single_process_emulation():
         # (1) the rank's own first-step gradients: same kernels on the same data in both runs -- only the order of
         # floating-point atomics differs
         for key in ("g", "d"):
+            top = max(v.double().norm().item() for v in ref_local[r][key].values())
             for k, v in ref_local[r][key].items():
+                if v.double().norm().item() < 1e-4 * top:
+                    continue   # conv bias in front of a BatchNorm: mathematically zero gradient, only rounding noise
                 got = res["local_grads"][key][k].to(dev).double()
                 e = (got - v.double()).norm().item() / (v.double().norm().item() or 1.0)
                 if e > worst_grad[0]:
