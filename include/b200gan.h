@@ -292,23 +292,33 @@ int b200gan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, d
  * a_l; the normalised tensor x_{l+1} = BN_l(a_l) is applied while the consumer gathers its operands and is never
  * written.  A BatchNorm seen from these kernels is the raw batch statistics plus its parameters: */
 typedef struct b200gan_nb_bn {
-  const double *stats; /* [2][C] sum, sum of squares of the normalised tensor over N*H*W; NULL = no BatchNorm */
+  const double *stats; /* [groups][2][C] sum, sum of squares of the normalised tensor over a group's N*H*W; NULL = no
+                          BatchNorm */
   const float *gamma;  /* [C] or NULL (= 1) */
   const float *beta;   /* [C] or NULL (= 0) */
   float eps;
-  double count;        /* N*H*W */
+  double count;        /* (N / groups)*H*W */
+  int32_t groups;      /* <= 1: the whole batch is one BatchNorm batch.  G > 1: the batch is G equal runs of images with
+                          independent batch statistics and weight gradients summed over all of them -- G forward passes of
+                          the reference (dcgan.py:178-179: discriminator(real_imgs), discriminator(gen_imgs.detach())) in
+                          one launch per layer; running statistics are updated G times in batch order.  Every stats / sums
+                          buffer of the chain entry points then has a leading [groups] dimension. */
+  int32_t reserved;
 } b200gan_nb_bn;
 /* 1 if the geometry can run in the fused chain (Conv2d, zero padding, stride 1/2, 3x3 or 4x4, C <= 128 (1 or a
  * multiple of 4), K a power of two in [4, 128]) */
 int b200gan_nb_supported(const b200gan_conv_geom *g);
+/* ... and with the batch split into `groups` statistics groups (see b200gan_nb_bn) */
+int b200gan_nb_groups_supported(const b200gan_conv_geom *g, int32_t groups);
 /* y = chan_scale[n,k] * act(conv(BN_in(x)) + bias): x = a_{l-1} [N][H][W][C]; packed = B200GAN_PACK_SIMT_FPROP.
  * in_bn (may be NULL): the BatchNorm between the producer and this conv, finalised in the prologue; running_mean/var and
- * num_batches_tracked (may be NULL) are updated once per call with torch semantics.  out_stats [2][K] (may be NULL):
+ * num_batches_tracked (may be NULL) are updated once per call (per group, in order) with torch semantics.  groups: see
+ * b200gan_nb_bn (must equal in_bn->groups when in_bn is given).  out_stats [groups][2][K] (may be NULL):
  * OVERWRITTEN with the batch sums of y for the next BatchNorm. */
 int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, float *running_mean, float *running_var,
                      int64_t *num_batches_tracked, float momentum, const float *x, const float *packed,
                      const float *bias, int32_t act, float slope, const float *chan_scale, float *y,
-                     double *out_stats, void *stream);
+                     double *out_stats, int32_t groups, void *stream);
 /* dz = BN_out-backward(g) * chan_scale * act'(a) and db[K] = column sums of dz (may be NULL).  g: gradient w.r.t. the
  * (virtual) BatchNorm output, or w.r.t. a itself when out_bn is NULL; sums [2][K]: sum g, sum g * ahat (complete). */
 int b200gan_nb_dz(int32_t N, int64_t PQ, int32_t K, const float *g, const float *a, const float *chan_scale,

@@ -47,7 +47,8 @@ class PackJob(ctypes.Structure):
 
 
 class NbBn(ctypes.Structure):
-    _fields_ = [("stats", c_vp), ("gamma", c_vp), ("beta", c_vp), ("eps", c_f32), ("count", c_f64)]
+    _fields_ = [("stats", c_vp), ("gamma", c_vp), ("beta", c_vp), ("eps", c_f32), ("count", c_f64), ("groups", c_i32),
+                ("reserved", c_i32)]
 
 
 class TailDesc(ctypes.Structure):
@@ -97,8 +98,9 @@ SIGNATURES = {
     "b200gan_critic_step_mlp": (c_i32, [_P(GpMlpDesc)] + [c_vp] * 18),
     "b200gan_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f32, c_vp, c_vp]),
     "b200gan_nb_supported": (c_i32, [_P(ConvGeom)]),
+    "b200gan_nb_groups_supported": (c_i32, [_P(ConvGeom), c_i32]),
     "b200gan_nb_fprop": (c_i32, [_P(ConvGeom), _P(NbBn), c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_i32, c_f32, c_vp,
-                                 c_vp, c_vp, c_vp]),
+                                 c_vp, c_vp, c_i32, c_vp]),
     "b200gan_nb_dz": (c_i32, [c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_f32, _P(NbBn), c_vp, c_vp, c_vp, c_vp]),
     "b200gan_nb_wgrad_workspace_floats": (c_sz, [_P(ConvGeom)]),
     "b200gan_nb_wgrad": (c_i32, [_P(ConvGeom), _P(NbBn), c_vp, c_vp, c_vp, c_vp, c_vp]),

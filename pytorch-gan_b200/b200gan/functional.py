@@ -472,6 +472,7 @@ class NbSpec:
     slope: float = 0.0
     momentum: float = 0.0     # of the BatchNorm on the INPUT edge (its running statistics are updated by this conv)
     want_stats: bool = False  # a training-mode BatchNorm follows: produce the batch sums of the output
+    groups: int = 1           # statistics groups of the batch (ops.bn_groups)
 
 
 class NbConvFn(torch.autograd.Function):
@@ -492,7 +493,7 @@ class NbConvFn(torch.autograd.Function):
         w = weight.detach()
         packed = cache.get(g, w, PACK_SIMT_FPROP)
         y, stats = ops.nb_fprop(g, x, packed, None if bias is None else bias.detach(), spec.act, spec.slope, chan_scale,
-                                in_edge, in_rm, in_rv, in_nbt, spec.momentum, spec.want_stats)
+                                in_edge, in_rm, in_rv, in_nbt, spec.momentum, spec.want_stats, spec.groups)
         ctx.g, ctx.spec, ctx.cache, ctx.in_edge, ctx.out_box = g, spec, cache, in_edge, out_box
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y, chan_scale)
@@ -541,7 +542,8 @@ class NbConvFn(torch.autograd.Function):
                 in_edge.sums = sums
                 c = g.C
                 if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
-                    dgb = sums.float()          # one conversion kernel for both parameter gradients
+                    # one conversion kernel for both parameter gradients (summed over the statistics groups)
+                    dgb = sums.float() if in_edge.groups == 1 else sums.view(in_edge.groups, 2 * c).sum(0).float()
                     dgamma = dgb[c:] if ctx.needs_input_grad[4] else None
                     dbeta = dgb[:c] if ctx.needs_input_grad[5] else None
         return gx, dw, db, None, dgamma, dbeta, None, None, None, None, None, None, None
@@ -569,7 +571,8 @@ class NbTailFn(torch.autograd.Function):
         c = a.shape[1]
         dgamma = dbeta = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            dgb = sums.float()
+            grp = ctx.edge.groups
+            dgb = sums.float() if grp == 1 else sums.view(grp, 2 * c).sum(0).float()
             dgamma = dgb[c:] if ctx.needs_input_grad[1] else None
             dbeta = dgb[:c] if ctx.needs_input_grad[2] else None
         return g, dgamma, dbeta, None, None, None, None, None, None

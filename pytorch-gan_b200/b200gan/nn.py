@@ -90,6 +90,13 @@ def _tc_like(conv, up, full=False):
             and conv.in_channels % 32 == 0 and conv.out_channels < 32)
 
 
+def _no_groups(what):
+    """ops.bn_groups is honoured by the fused chain only: anything else that depends on the batch composition refuses."""
+    if ops.bn_groups.active > 1:
+        raise RuntimeError(f"b200gan: ops.bn_groups({ops.bn_groups.active}) is active but {what} would treat the batch "
+                           "as one pass; run the passes separately")
+
+
 def _dropout2d_scale(x_shape, p, device):
     """Exactly the draw F.dropout2d makes (feature_dropout: noise [N,C,1,1] ~ Bernoulli(1-p) / (1-p)),
     so masks are bit-identical to the reference's under the same seed (dcgan.py:77)."""
@@ -132,6 +139,8 @@ def _run_norm(norm, x, act=ACT_NONE, slope=0.0, stats=None, rtf_out=False, rtf_d
     if per_sample and x.shape[2] * x.shape[3] == 1 and norm.training:
         raise ValueError(f"Expected more than 1 spatial element when training, got input size {tuple(x.shape)}")
     use_batch_stats = per_sample or norm.training or norm.running_mean is None
+    if use_batch_stats and not per_sample:
+        _no_groups("a stand-alone BatchNorm2d")
     if use_batch_stats:
         rm = rv = nbt = None
         momentum = 0.0
@@ -234,6 +243,7 @@ class Dropout2d(_T["Dropout2d"]):
             return super().forward(x)
         if not self.training or self.p == 0.0:
             return x
+        _no_groups("a stand-alone Dropout2d")
         return F.ActFn.apply(x, ACT_NONE, 0.0, _dropout2d_scale(x.shape, self.p, x.device), True)
 
 
@@ -243,6 +253,7 @@ class Dropout(_T["Dropout"]):
             return super().forward(x)
         if not self.training or self.p == 0.0:
             return x
+        _no_groups("a stand-alone Dropout")
         xc = x if ops.is_cl(x) else ops.to_cl(x)
         mask = torch.empty_like(xc, memory_format=torch.channels_last)
         if self.p >= 1.0:
@@ -310,6 +321,47 @@ class _TailStep:
 
     def __init__(self, norm_step, conv_step):
         self.norm_step, self.conv_step = norm_step, conv_step
+
+
+def _chain_plan(chain, shape):
+    """[(conv step, norm step, output shape)] if every layer of the chain qualifies for the fused kernels at this input
+    shape (and under the active ops.bn_groups), else None.  No side effects."""
+    plan = []
+    for cs, ns in chain.layers:
+        conv = cs.conv
+        if shape[1] != conv.in_channels or not _conv_ok(conv):
+            return None
+        g, oshape = ops.make_geom(shape, tuple(conv.weight.shape), int(conv.stride[0]), (int(conv.padding[0]),) * 4)
+        macs = float(oshape[0]) * oshape[2] * oshape[3] * conv.out_channels * conv.in_channels * g.R * g.S
+        if macs > _ChainStep.MAX_MACS or not ops.nb_supported(g) or oshape[2] * oshape[3] < 1:
+            return None
+        if ns is not None:
+            norm = ns.norm
+            if not (norm.training and norm.num_features == conv.out_channels):
+                return None
+            if norm.track_running_stats and norm.momentum is None:
+                return None
+        plan.append((cs, ns, oshape))
+        shape = oshape
+    return plan
+
+
+def groups_eligible(seq, x_shape, groups):
+    """True if the drop-in Sequential `seq` would take a [N, C, H, W] fp32 CUDA batch of `groups` statistics groups
+    entirely through fused chains (the only code that honours ops.bn_groups)."""
+    if not isinstance(seq, Sequential) or not ops.Config.fuse_narrow_chain or x_shape[0] % groups != 0:
+        return False
+    steps = seq._plan()
+    if not steps or not all(isinstance(st, _ChainStep) for st in steps):
+        return False
+    shape = tuple(x_shape)
+    with ops.bn_groups(groups):
+        for st in steps:
+            plan = _chain_plan(st, shape)
+            if plan is None:
+                return False
+            shape = plan[-1][2]
+    return True
 
 
 class _ChainStep:
@@ -479,29 +531,24 @@ class Sequential(_T["Sequential"]):
         if not ops.Config.fuse_narrow_chain or ops.Config.algo == "simt_generic":
             return None
         shape = tuple(x.shape)
-        plan = []
-        for cs, ns in chain.layers:
-            conv = cs.conv
-            if shape[1] != conv.in_channels or not _conv_ok(conv):
-                return None
-            g, oshape = ops.make_geom(shape, tuple(conv.weight.shape), int(conv.stride[0]), (int(conv.padding[0]),) * 4)
-            macs = float(oshape[0]) * oshape[2] * oshape[3] * conv.out_channels * conv.in_channels * g.R * g.S
-            if macs > _ChainStep.MAX_MACS or not ops.nb_supported(g) or oshape[2] * oshape[3] < 1:
-                return None
-            if ns is not None:
-                norm = ns.norm
-                if not (norm.training and norm.num_features == conv.out_channels):
-                    return None
-                if norm.track_running_stats and norm.momentum is None:
-                    return None
-            plan.append((cs, ns, oshape))
-            shape = oshape
+        plan = _chain_plan(chain, shape)
+        if plan is None:
+            return None
+        groups = ops.bn_groups.active
+        if groups > 1 and shape[0] % groups != 0:
+            raise RuntimeError("b200gan: ops.bn_groups: the batch does not split evenly into the groups")
+        # Dropout2d masks.  One pass: drawn layer by layer as F.dropout2d does.  G statistics groups = G forward passes of
+        # the reference: pass 0 draws all its layers' masks, then pass 1, ... -- drawn up front in that order.
+        scales = [None] * len(plan)
+        for gq in range(groups):
+            for li, (cs, ns, oshape) in enumerate(plan):
+                if cs.dropout2d is not None and cs.dropout2d.training and cs.dropout2d.p > 0.0:
+                    part = _dropout2d_scale((x.shape[0] // groups, cs.conv.out_channels), cs.dropout2d.p, x.device)
+                    scales[li] = part if scales[li] is None else torch.cat([scales[li], part])
         edge, prev_norm = None, None
-        for cs, ns, oshape in plan:
+        for li, (cs, ns, oshape) in enumerate(plan):
             conv = cs.conv
-            scale = None
-            if cs.dropout2d is not None and cs.dropout2d.training and cs.dropout2d.p > 0.0:
-                scale = _dropout2d_scale((x.shape[0], conv.out_channels), cs.dropout2d.p, x.device)
+            scale = scales[li]
             gam = bet = rm = rv = nbt = None
             momentum = 0.0
             if prev_norm is not None:
@@ -510,7 +557,7 @@ class Sequential(_T["Sequential"]):
                     rm, rv, nbt = prev_norm.running_mean, prev_norm.running_var, prev_norm.num_batches_tracked
                     momentum = float(prev_norm.momentum)
             spec = F.NbSpec(stride=int(conv.stride[0]), pad=int(conv.padding[0]), act=cs.act, slope=cs.slope,
-                            momentum=momentum, want_stats=ns is not None)
+                            momentum=momentum, want_stats=ns is not None, groups=groups)
             cache = conv.__dict__.get("_b200_cache")
             if cache is None:
                 cache = PackCache()
@@ -522,7 +569,7 @@ class Sequential(_T["Sequential"]):
                 norm = ns.norm
                 edge = ops.BnEdge(stats, None if norm.weight is None else norm.weight.detach(),
                                   None if norm.bias is None else norm.bias.detach(), norm.eps,
-                                  oshape[0] * oshape[2] * oshape[3])
+                                  oshape[0] // groups * oshape[2] * oshape[3], groups)
                 out_box.append(edge)
                 prev_norm = norm
             else:
@@ -572,6 +619,7 @@ class Sequential(_T["Sequential"]):
                 at_end = not queue
                 res = self._run_chain(s, x, want_contiguous and at_end)
                 if res is None:
+                    _no_groups("a conv chain that does not qualify for the fused kernels")
                     queue[0:0] = s.steps
                 else:
                     x, stats = res, None
@@ -581,6 +629,7 @@ class Sequential(_T["Sequential"]):
             if isinstance(s, _TailStep):
                 ns, cs = s.norm_step, s.conv_step
                 norm, conv = ns.norm, cs.conv
+                _no_groups("the fused generator tail")
                 if (norm.training and x.shape[1] == conv.in_channels and x.shape[1] == norm.num_features
                         and ops.tail_supported(tuple(x.shape), conv.out_channels, ns.act, ns.slope, cs.act)):
                     rm = rv = nbt = None
@@ -600,6 +649,7 @@ class Sequential(_T["Sequential"]):
             if isinstance(s, _ConvStep):
                 cs = None
                 if s.dropout2d is not None and s.dropout2d.training and s.dropout2d.p > 0.0:
+                    _no_groups("a Dropout2d outside a fused chain")
                     n = x.shape[0]
                     cs = _dropout2d_scale((n, s.conv.out_channels), s.dropout2d.p, x.device)
                 # fused statistics only when the following norm really normalises with batch statistics (an eval-mode

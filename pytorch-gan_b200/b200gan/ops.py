@@ -27,6 +27,8 @@ class Config:
     fuse_tail = os.environ.get("B200GAN_FUSE_TAIL", "1") not in ("", "0")
     # [Conv2d -> LeakyReLU -> Dropout2d -> BatchNorm2d] runs of narrow layers as the fused chain (csrc/narrow_block.cu)
     fuse_narrow_chain = os.environ.get("B200GAN_FUSE_CHAIN", "1") not in ("", "0")
+    # train.dcgan_step: discriminator(real) and discriminator(fake) as ONE grouped pass through the fused chain
+    batch_d_passes = os.environ.get("B200GAN_BATCH_D", "1") not in ("", "0")
     # norm kernels: fixed-channel-group fast paths (csrc/norm.cu) and activation mask recomputed from x in backward
     norm_fast = os.environ.get("B200GAN_NORM_FAST", "1") not in ("", "0")
 
@@ -378,33 +380,62 @@ class BnEdge:
     """A training-mode BatchNorm2d between two fused convs: its batch statistics (fp64 sums of the producer's output)
     and parameters.  `sums` is filled by the consumer's backward (sum g, sum g * ahat) for the producer's backward."""
 
-    def __init__(self, stats, gamma, beta, eps, count):
+    def __init__(self, stats, gamma, beta, eps, count, groups=1):
+        """stats: [groups][2][C] fp64; count: elements per channel and group (see b200gan_nb_bn in include/b200gan.h)."""
         self.stats, self.gamma, self.beta, self.eps, self.count = stats, gamma, beta, float(eps), float(count)
+        self.groups = int(groups)
         self.sums = None
 
     def c_struct(self):
         b = NbBn()
         b.stats, b.gamma, b.beta = self.stats.data_ptr(), _ptr(self.gamma), _ptr(self.beta)
-        b.eps, b.count = self.eps, self.count
+        b.eps, b.count, b.groups, b.reserved = self.eps, self.count, self.groups, 0
         return b
 
 
+class bn_groups:
+    """`with ops.bn_groups(G):` -- the batch entering the drop-in modules is G equal runs of images that are to be treated
+    as G separate forward passes of the reference sharing the weights: independent BatchNorm batch statistics (running
+    statistics updated G times, in order), Dropout2d masks drawn in the order of G separate passes, parameter gradients
+    summed.  Used by train.dcgan_step to run discriminator(real_imgs) and discriminator(gen_imgs.detach())
+    (dcgan.py:178-179) as one launch per layer.  Only the fused chain honours it: every other normalisation /
+    dropout module raises while it is active (train.py checks eligibility first)."""
+
+    active = 1
+
+    def __init__(self, groups):
+        self.groups = int(groups)
+
+    def __enter__(self):
+        self.prev = bn_groups.active
+        bn_groups.active = self.groups
+        return self
+
+    def __exit__(self, *exc):
+        bn_groups.active = self.prev
+
+
 def nb_supported(g):
-    if not Config.fuse_narrow_chain or not bool(_lib.load().b200gan_nb_supported(ctypes.byref(g))):
+    if not Config.fuse_narrow_chain:
         return False
-    return True
+    lib = _lib.load()
+    if bn_groups.active > 1:
+        return bool(lib.b200gan_nb_groups_supported(ctypes.byref(g), bn_groups.active))
+    return bool(lib.b200gan_nb_supported(ctypes.byref(g)))
 
 
 def _bn_ref(edge):
     return ctypes.byref(edge.c_struct()) if edge is not None else None
 
 
-def nb_fprop(g, x, packed, bias, act, slope, chan_scale, in_edge, running_mean, running_var, nbt, momentum, want_stats):
+def nb_fprop(g, x, packed, bias, act, slope, chan_scale, in_edge, running_mean, running_var, nbt, momentum, want_stats,
+             groups=1):
     y = empty_cl(g.N, g.K, g.P, g.Q, x.device)
-    stats = torch.empty(2 * g.K, device=x.device, dtype=torch.float64) if want_stats else None
+    stats = torch.empty(groups * 2 * g.K, device=x.device, dtype=torch.float64) if want_stats else None
     _lib.check(_lib.load().b200gan_nb_fprop(ctypes.byref(g), _bn_ref(in_edge), _ptr(running_mean), _ptr(running_var),
                                             _ptr(nbt), float(momentum), x.data_ptr(), packed.data_ptr(), _ptr(bias),
-                                            act, slope, _ptr(chan_scale), y.data_ptr(), _ptr(stats), _stream()), "nb_fprop")
+                                            act, slope, _ptr(chan_scale), y.data_ptr(), _ptr(stats), int(groups),
+                                            _stream()), "nb_fprop")
     return y, stats
 
 
@@ -430,7 +461,8 @@ def nb_wgrad(g, x, dz, in_edge, weight_shape):
 
 def nb_dgrad(g, dz, packed, in_edge, a_prev):
     gout = empty_cl(g.N, g.C, g.H, g.W, dz.device)
-    sums = torch.empty(2 * g.C, device=dz.device, dtype=torch.float64) if in_edge is not None else None
+    sums = (torch.empty(in_edge.groups * 2 * g.C, device=dz.device, dtype=torch.float64)
+            if in_edge is not None else None)
     _lib.check(_lib.load().b200gan_nb_dgrad(ctypes.byref(g), dz.data_ptr(), packed.data_ptr(), _bn_ref(in_edge),
                                             _ptr(a_prev) if in_edge is not None else 0, gout.data_ptr(), _ptr(sums),
                                             _stream()), "nb_dgrad")
@@ -452,7 +484,7 @@ def nb_tail_fwd(a, edge, running_mean, running_var, nbt, momentum, nchw):
 def nb_tail_bwd(a, edge, dout, nchw):
     n, c, h, w = a.shape
     g = torch.empty_like(a, memory_format=CL)
-    sums = torch.empty(2 * c, device=a.device, dtype=torch.float64)
+    sums = torch.empty(edge.groups * 2 * c, device=a.device, dtype=torch.float64)
     _lib.check(_lib.load().b200gan_nb_tail_bwd(n, h * w, c, _bn_ref(edge), a.data_ptr(), dout.data_ptr(), int(nchw),
                                                g.data_ptr(), sums.data_ptr(), _stream()), "nb_tail_bwd")
     return g, sums

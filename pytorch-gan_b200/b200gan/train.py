@@ -39,6 +39,23 @@ def _join(*reducers):
             r.join()
 
 
+def _d_passes_batchable(discriminator, real_imgs, loss):
+    """The two discriminator passes of the D step can run as one grouped pass: a DCGAN-style module (`model` = conv blocks
+    that the fused chain covers completely, `adv_layer` without batch-dependent modules, zoo.DCGANDiscriminator /
+    dcgan.py:73-99), a mean-reduced element-wise loss, training mode."""
+    from . import nn as bnn
+    if not ops.Config.batch_d_passes or not getattr(discriminator, "_b200_batchable_passes", False):
+        return False
+    if not (discriminator.training and real_imgs.is_cuda and real_imgs.dim() == 4 and real_imgs.dtype == torch.float32):
+        return False
+    if not isinstance(loss, (torch.nn.BCELoss, torch.nn.MSELoss)) or loss.reduction != "mean":
+        return False
+    if getattr(loss, "weight", None) is not None:
+        return False
+    shape = (2 * real_imgs.shape[0],) + tuple(real_imgs.shape[1:])
+    return bnn.groups_eligible(discriminator.model, shape, 2)
+
+
 def dcgan_step(generator, discriminator, opt_g, opt_d, real_imgs, z, loss=None, valid=None, fake=None,
                reduce_g=None, reduce_d=None, skip_dead_wgrad=True):
     """implementations/dcgan/dcgan.py:146-183.  `reduce_*`: optional gradient all-reduce hooks invoked
@@ -55,9 +72,17 @@ def dcgan_step(generator, discriminator, opt_g, opt_d, real_imgs, z, loss=None, 
         g_loss.backward()                                    # :168
     _opt_step(opt_g, reduce_g)                               # :169 (all-reduce + Adam may overlap the D phase below)
     opt_d.zero_grad()                                        # :175
-    real_loss = loss(discriminator(real_imgs), valid)        # :178
-    fake_loss = loss(discriminator(gen_imgs.detach()), fake) # :179
-    d_loss = (real_loss + fake_loss) / 2                     # :180
+    if _d_passes_batchable(discriminator, real_imgs, loss):
+        # :178-180 as ONE pass over [real; fake] with two BatchNorm statistics groups (ops.bn_groups): same batch
+        # statistics, running-statistics updates, dropout masks and summed parameter gradients as the two passes, half the
+        # launches.  mean over 2N outputs == (mean over real + mean over fake) / 2.
+        with ops.bn_groups(2):
+            out = discriminator(torch.cat([real_imgs, gen_imgs.detach()]))
+        d_loss = loss(out, torch.cat([valid, fake]))
+    else:
+        real_loss = loss(discriminator(real_imgs), valid)        # :178
+        fake_loss = loss(discriminator(gen_imgs.detach()), fake) # :179
+        d_loss = (real_loss + fake_loss) / 2                     # :180
     d_loss.backward()                                        # :182
     _opt_step(opt_d, reduce_d)                               # :183
     _join(reduce_g, reduce_d)

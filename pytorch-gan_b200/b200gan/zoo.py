@@ -64,6 +64,10 @@ class DCGANGenerator(tnn.Module):
 class DCGANDiscriminator(tnn.Module):
     """dcgan/dcgan.py:73-99."""
 
+    # forward = conv blocks -> view -> Linear + Sigmoid, nothing batch-dependent outside `model`: train.dcgan_step may run
+    # the real and the fake pass of the D step as one grouped pass (ops.bn_groups)
+    _b200_batchable_passes = True
+
     def __init__(self, img_size=64, channels=1, nn=None):
         super().__init__()
         nn = nn or namespace()

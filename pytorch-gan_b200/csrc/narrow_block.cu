@@ -27,16 +27,19 @@
 namespace b200gan {
 
 struct NbBn {
-  const double *stats;  // [2][C]: sum, sum of squares over the batch (null: no BatchNorm on this edge)
+  const double *stats;  // [groups][2][C]: sum, sum of squares over a group's batch (null: no BatchNorm on this edge)
   const float *gamma, *beta;
   float eps;
-  double count;
+  double count;         // elements per channel and GROUP
+  int groups;           // the batch is `groups` equal runs of images with independent statistics (train.dcgan_step:
+                        // the discriminator's real and fake passes of dcgan.py:178-179 in one launch per layer)
 };
 
 __device__ __forceinline__ void nb_bn_consts(const NbBn &bn, int C, int c, float &mean, float &rstd, float &sc,
-                                             float &sh, double *var_out = nullptr) {
-  const double m = bn.stats[c] / bn.count;
-  double var = bn.stats[C + c] / bn.count - m * m;
+                                             float &sh, double *var_out = nullptr, int grp = 0) {
+  const double *st = bn.stats + (size_t)grp * 2 * C;
+  const double m = st[c] / bn.count;
+  double var = st[C + c] / bn.count - m * m;
   if (var < 0.0) var = 0.0;
   if (var_out) *var_out = var;
   rstd = (float)(1.0 / sqrt(var + (double)bn.eps));
@@ -46,13 +49,19 @@ __device__ __forceinline__ void nb_bn_consts(const NbBn &bn, int C, int c, float
   sh = be - mean * sc;
 }
 
+// running statistics: one update per group, in batch order (= the order of the reference's separate forward passes)
 __device__ __forceinline__ void nb_update_running(const NbBn &bn, int C, int c, float *rm, float *rv, float momentum) {
-  float mean, rstd, sc, sh;
-  double var;
-  nb_bn_consts(bn, C, c, mean, rstd, sc, sh, &var);
-  const double unbiased = bn.count > 1.0 ? var * bn.count / (bn.count - 1.0) : var;
-  rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
-  rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+  float m_run = rm[c], v_run = rv[c];
+  for (int grp = 0; grp < bn.groups; ++grp) {
+    float mean, rstd, sc, sh;
+    double var;
+    nb_bn_consts(bn, C, c, mean, rstd, sc, sh, &var, grp);
+    const double unbiased = bn.count > 1.0 ? var * bn.count / (bn.count - 1.0) : var;
+    m_run = (1.f - momentum) * m_run + momentum * mean;
+    v_run = (1.f - momentum) * v_run + momentum * (float)unbiased;
+  }
+  rm[c] = m_run;
+  rv[c] = v_run;
 }
 
 __device__ __forceinline__ float nb_act(float v, int act, float slope) {
@@ -75,6 +84,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 constexpr int NB_MAXC = 128;
+constexpr int NB_MAX_GROUPS = 4;   // statistics groups per batch (NbBn::groups)
 
 // ---- forward ------------------------------------------------------------------------------------------------------
 struct NbFprop {
@@ -274,6 +284,7 @@ struct NbFprop2 {
   int PR, PC, CP;   // patch rows, columns, channel pitch (C + 4: lanes = pixels 2 * CP floats apart stay 2-way conflicted at worst)
   int reflect;      // reflection padding (stand-alone use: cyclegan/models.py:49-50), chains are zero-padded
   int rtf;          // store y rounded to TF32 (a tcgen05 conv consumes it next)
+  int groups;       // statistics groups of the batch (NbBn::groups of the edges; 1 stand-alone)
 };
 // Forward: the patch (BatchNorm of the producer applied while staging) and this block's slice of the weights live in
 // shared memory.  Thread = PT pixels x KT output channels in registers: lanes of a warp are consecutive pixels (pixel i
@@ -293,16 +304,18 @@ nbk_fprop2_kernel(const __grid_constant__ NbFprop2 p) {
   float *red = sh_s + ((p.C + 3) & ~3);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_in = p.in_bn.stats != nullptr;
+  // the tile's images belong to ONE statistics group (the planner keeps TN a divisor of the group size)
+  const int grp = (int)((blockIdx.x / (t.tiles_q * t.tiles_r)) * t.TN) / (p.N / p.groups);
   for (int cc = tid; cc < p.C; cc += 256) {
     float mean, rstd, sc = 1.f, sh = 0.f;
     if (has_in) {
-      nb_bn_consts(p.in_bn, p.C, cc, mean, rstd, sc, sh);
+      nb_bn_consts(p.in_bn, p.C, cc, mean, rstd, sc, sh, nullptr, grp);
       if (blockIdx.x == 0 && blockIdx.y == 0 && p.rm) nb_update_running(p.in_bn, p.C, cc, p.rm, p.rv, p.momentum);
     }
     sc_s[cc] = sc;
     sh_s[cc] = sh;
   }
-  if (has_in && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && p.nbt) *p.nbt += 1;
+  if (has_in && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && p.nbt) *p.nbt += p.in_bn.groups;
   // this block's weights: rows (tap, c) of KB consecutive output channels
   const int kbase = blockIdx.y * t.KB;
   {
@@ -440,7 +453,7 @@ nbk_fprop2_kernel(const __grid_constant__ NbFprop2 p) {
       const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = TPX >> 5;
       float tsum = 0.f;
       for (int wi = 0; wi < wpg; ++wi) tsum += red[(g * wpg + wi) * 2 * KT + idx];
-      atomicAdd(p.out_stats + (idx < KT ? 0 : p.K) + kbase + g * KT + (idx % KT), (double)tsum);
+      atomicAdd(p.out_stats + (size_t)grp * 2 * p.K + (idx < KT ? 0 : p.K) + kbase + g * KT + (idx % KT), (double)tsum);
     }
   }
 }
@@ -465,19 +478,22 @@ nbk_dz_kernel(const __grid_constant__ NbDz p) {
   const int kq = tid % K4;
   const int rows_per_block = 256 / K4;
   const bool has_bn = p.out_bn.stats != nullptr;
+  const int grp = blockIdx.y;                                  // statistics group = a contiguous run of rows
+  const int64_t grows = p.rows / gridDim.y, grow0 = grp * grows;
   float mean[4], rstd[4], sc[4], m1[4], m2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     mean[j] = 0.f; rstd[j] = 0.f; sc[j] = 1.f; m1[j] = 0.f; m2[j] = 0.f;
     if (has_bn) {
       float sh;
-      nb_bn_consts(p.out_bn, p.K, kq * 4 + j, mean[j], rstd[j], sc[j], sh);
-      m1[j] = (float)(p.sums[kq * 4 + j] / p.out_bn.count);
-      m2[j] = (float)(p.sums[p.K + kq * 4 + j] / p.out_bn.count);
+      nb_bn_consts(p.out_bn, p.K, kq * 4 + j, mean[j], rstd[j], sc[j], sh, nullptr, grp);
+      m1[j] = (float)(p.sums[(size_t)grp * 2 * p.K + kq * 4 + j] / p.out_bn.count);
+      m2[j] = (float)(p.sums[(size_t)grp * 2 * p.K + p.K + kq * 4 + j] / p.out_bn.count);
     }
   }
   float dbs[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + tid / K4; row < p.rows;
+  const int64_t row_end = grow0 + grows;
+  for (int64_t row = grow0 + (int64_t)blockIdx.x * rows_per_block + tid / K4; row < row_end;
        row += (int64_t)gridDim.x * rows_per_block) {
     const int64_t off = row * p.K + kq * 4;
     const float4 gv = __ldg(reinterpret_cast<const float4 *>(p.g + off));
@@ -543,15 +559,18 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   int *poff_s = sk_s + p.SPB;
   float *x_s = nsm + ((2 * p.SPB + tile_px + 3) & ~3);
   float *dz_s = x_s + (((size_t)p.TN * patch_img + 3) & ~(size_t)3);
-  float *sc_s = dz_s + (size_t)tile_px * KP;
-  float *sh_s = sc_s + ((p.C + 3) & ~3);
+  const int Cr = (p.C + 3) & ~3;
+  const int groups = p.in_bn.groups, img_per_group = p.N / groups;
+  float *sc_s = dz_s + (size_t)tile_px * KP;    // [groups][Cr]
+  float *sh_s = sc_s + (size_t)groups * Cr;     // [groups][Cr]
   const int tid = threadIdx.x;
   const bool has_in = p.in_bn.stats != nullptr;
-  for (int cc = tid; cc < p.C; cc += 256) {
+  for (int i = tid; i < groups * p.C; i += 256) {
+    const int gq = i / p.C, cc = i - gq * p.C;
     float mean, rstd, sc = 1.f, sh = 0.f;
-    if (has_in) nb_bn_consts(p.in_bn, p.C, cc, mean, rstd, sc, sh);
-    sc_s[cc] = sc;
-    sh_s[cc] = sh;
+    if (has_in) nb_bn_consts(p.in_bn, p.C, cc, mean, rstd, sc, sh, nullptr, gq);
+    sc_s[gq * Cr + cc] = sc;
+    sh_s[gq * Cr + cc] = sh;
   }
   // the integer divisions happen once per block, not once per pixel / output value
   for (int pix = tid; pix < tile_px; pix += 256) {
@@ -595,8 +614,9 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
     const int h0 = p0 * p.stride - p.pad_t, w0 = q0 * p.stride - p.pad_l;
     for (int li = 0; li < p.TN; ++li) {
       const int n = n0 + li;
+      const int gq = n < p.N ? n / img_per_group : 0;
       nb_stage(x_s + (size_t)li * patch_img, p.C, n < p.N ? p.x + (int64_t)n * p.H * p.W * p.C : nullptr, h0, w0, p.PR, p.PC,
-               p.C, p.H, p.W, has_in ? sc_s : nullptr, sh_s, p.reflect != 0, tid);
+               p.C, p.H, p.W, has_in ? sc_s + gq * Cr : nullptr, sh_s + gq * Cr, p.reflect != 0, tid);
     }
     const int img_px = p.TR * p.TQ;
     if ((p.K & 3) == 0) {
@@ -833,10 +853,12 @@ nbk_dgrad2_kernel(const __grid_constant__ NbDgrad2 p) {
   float *red = rstd_s + ((p.C + 3) & ~3);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_in = p.sums != nullptr;
+  // one statistics group per tile (the planner keeps TN a divisor of the group size)
+  const int grp = (int)((blockIdx.x / (t.tiles_q * t.tiles_r)) * t.TN) / (p.N / p.in_bn.groups);
   if (has_in) {
     for (int cc = tid; cc < p.C; cc += 256) {
       float sc, sh;
-      nb_bn_consts(p.in_bn, p.C, cc, mean_s[cc], rstd_s[cc], sc, sh);
+      nb_bn_consts(p.in_bn, p.C, cc, mean_s[cc], rstd_s[cc], sc, sh, nullptr, grp);
     }
   }
   const int st = p.stride;
@@ -989,7 +1011,7 @@ nbk_dgrad2_kernel(const __grid_constant__ NbDgrad2 p) {
       const int g = tid / (2 * KT), idx = tid % (2 * KT), wpg = TPX >> 5;
       float tsum = 0.f;
       for (int wi = 0; wi < wpg; ++wi) tsum += red[(g * wpg + wi) * 2 * KT + idx];
-      atomicAdd(p.sums + (idx < KT ? 0 : p.C) + cbase + g * KT + (idx % KT), (double)tsum);
+      atomicAdd(p.sums + (size_t)grp * 2 * p.C + (idx < KT ? 0 : p.C) + cbase + g * KT + (idx % KT), (double)tsum);
     }
   }
 }
@@ -1011,15 +1033,16 @@ __global__ void __launch_bounds__(256)
 nbk_tail_fwd_kernel(const __grid_constant__ NbTail p) {
   __shared__ float sc_s[NB_MAXC], sh_s[NB_MAXC];
   const int tid = threadIdx.x;
+  const int grp = blockIdx.y;   // statistics group = a contiguous run of images
   if (tid < p.C) {
     float mean, rstd;
-    nb_bn_consts(p.bn, p.C, tid, mean, rstd, sc_s[tid], sh_s[tid]);
-    if (blockIdx.x == 0 && p.rm) nb_update_running(p.bn, p.C, tid, p.rm, p.rv, p.momentum);
+    nb_bn_consts(p.bn, p.C, tid, mean, rstd, sc_s[tid], sh_s[tid], nullptr, grp);
+    if (blockIdx.x == 0 && grp == 0 && p.rm) nb_update_running(p.bn, p.C, tid, p.rm, p.rv, p.momentum);
   }
-  if (blockIdx.x == 0 && tid == 0 && p.nbt) *p.nbt += 1;
+  if (blockIdx.x == 0 && grp == 0 && tid == 0 && p.nbt) *p.nbt += p.bn.groups;
   __syncthreads();
-  const int64_t total = (int64_t)p.N * p.HW * p.C;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < total; i += (int64_t)gridDim.x * 256) {
+  const int64_t gtotal = (int64_t)(p.N / gridDim.y) * p.HW * p.C, total = (grp + 1) * gtotal;
+  for (int64_t i = grp * gtotal + (int64_t)blockIdx.x * 256 + tid; i < total; i += (int64_t)gridDim.x * 256) {
     int c;
     int64_t src;
     if (p.nchw) {  // i enumerates the OUTPUT [n][c][hw]
@@ -1040,15 +1063,17 @@ nbk_tail_bwd_kernel(const __grid_constant__ NbTail p) {
   __shared__ float mean_s[NB_MAXC], rstd_s[NB_MAXC];
   __shared__ float red[256][2];
   const int tid = threadIdx.x;
+  const int grp = blockIdx.y;
   if (tid < p.C) {
     float sc, sh;
-    nb_bn_consts(p.bn, p.C, tid, mean_s[tid], rstd_s[tid], sc, sh);
+    nb_bn_consts(p.bn, p.C, tid, mean_s[tid], rstd_s[tid], sc, sh, nullptr, grp);
   }
   __syncthreads();
-  const int64_t total = (int64_t)p.N * p.HW * p.C;
+  // a group's elements start at a multiple of C, so the channel of a thread is the same in every group
+  const int64_t gtotal = (int64_t)(p.N / gridDim.y) * p.HW * p.C, total = (grp + 1) * gtotal;
   const int c = (int)(((int64_t)blockIdx.x * 256 + tid) % p.C);
   float s1 = 0.f, s2 = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < total; i += (int64_t)gridDim.x * 256) {
+  for (int64_t i = grp * gtotal + (int64_t)blockIdx.x * 256 + tid; i < total; i += (int64_t)gridDim.x * 256) {
     int64_t src = i;   // i enumerates g [n][hw][c]
     if (p.nchw) {
       const int64_t row = i / p.C;
@@ -1072,8 +1097,8 @@ nbk_tail_bwd_kernel(const __grid_constant__ NbTail p) {
       t2 += red[j][1];
     }
     const int ch = (int)(((int64_t)blockIdx.x * 256 + tid) % p.C);
-    atomicAdd(p.sums + ch, (double)t1);
-    atomicAdd(p.sums + p.C + ch, (double)t2);
+    atomicAdd(p.sums + (size_t)grp * 2 * p.C + ch, (double)t1);
+    atomicAdd(p.sums + (size_t)grp * 2 * p.C + p.C + ch, (double)t2);
   }
 }
 
@@ -1084,6 +1109,7 @@ static NbBn to_bn(const b200gan_nb_bn *b) {
   r.beta = b ? b->beta : nullptr;
   r.eps = b ? b->eps : 0.f;
   r.count = b ? b->count : 1.0;
+  r.groups = (b && b->groups > 1) ? b->groups : 1;
   return r;
 }
 
@@ -1117,7 +1143,8 @@ struct NbPlan {
 // per 4 * PT * KT FMAs, against 4 FMA issue slots per cycle: max(1/4, (PT + KT) / (PT * KT)); divided by the SMs the
 // grid can fill.
 template <class F>
-static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, int nclasses, bool allow_pt, F patch) {
+static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, int nclasses, bool allow_pt, int groups,
+                      F patch) {
   NbPlan best;
   memset(&best, 0, sizeof(best));
   double best_cost = 1e30;
@@ -1140,6 +1167,7 @@ static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, in
         t.TR = pow2ceil(Ho) < t.TP / t.TQ ? pow2ceil(Ho) : t.TP / t.TQ;
         t.TN = t.TP / (t.TQ * t.TR);
         if (t.TN > 1 && t.TN / 2 >= N) continue;           // tile mostly empty: a smaller PT / larger KG fits better
+        if (groups > 1 && (N / groups) % t.TN != 0) continue;   // a tile must not straddle two statistics groups
         t.tiles_r = ceil_div(Ho, t.TR);
         t.tiles_q = ceil_div(Wo, t.TQ);
         const size_t floats = (size_t)((wrow * KB + 3) & ~(int64_t)3) + ((patch(t.TN, t.TR, t.TQ) + 3) & ~(size_t)3) +
@@ -1162,23 +1190,32 @@ static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, in
   }
   return best;
 }
-static NbPlan nb_plan_fprop(const b200gan_conv_geom *g) {
+static NbPlan nb_plan_fprop(const b200gan_conv_geom *g, int groups = 1) {
   const int CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
-  return nb_plan(g->K, (int64_t)g->R * g->S * g->C, g->C, g->N, g->P, g->Q, 1, g->R * g->S * g->C >= 16,
+  return nb_plan(g->K, (int64_t)g->R * g->S * g->C, g->C, g->N, g->P, g->Q, 1, g->R * g->S * g->C >= 16, groups,
                  [&](int TN, int TR, int TQ) {
     return (size_t)TN * ((TR - 1) * g->stride + g->R) * ((TQ - 1) * g->stride + g->S) * CP;
   });
 }
-static NbPlan nb_plan_dgrad(const b200gan_conv_geom *g) {
+static NbPlan nb_plan_dgrad(const b200gan_conv_geom *g, int groups = 1) {
   const int st = g->stride;
   const int Rm = ceil_div(g->R, st), Sm = ceil_div(g->S, st);
   return nb_plan(g->C, (int64_t)Rm * Sm * g->K, g->C, g->N, ceil_div(g->H, st), ceil_div(g->W, st), st * st, g->C >= 4,
-                 [&](int TN, int TR, int TQ) { return (size_t)TN * (TR + Rm - 1) * (TQ + Sm - 1) * (g->K + 4); });
+                 groups, [&](int TN, int TR, int TQ) { return (size_t)TN * (TR + Rm - 1) * (TQ + Sm - 1) * (g->K + 4); });
 }
 }  // namespace b200gan
 
 // geometry the fused chain takes: Conv2d, zero padding, no folded upsample, stride 1 or 2, <= 128 channels either side,
 // K a power of two >= 4 (the channel-group mappings above), fp32 SIMT, and a tile plan that fits in shared memory.
+extern "C" int b200gan_nb_supported(const b200gan_conv_geom *g);
+// the chain layer can run with `groups` statistics groups: a tile plan exists whose tiles stay inside one group
+extern "C" int b200gan_nb_groups_supported(const b200gan_conv_geom *g, int32_t groups) {
+  if (!b200gan_nb_supported(g)) return 0;
+  if (groups <= 1) return 1;
+  if (nb_v1() || groups > NB_MAX_GROUPS || g->N % groups != 0) return 0;
+  return nb_plan_fprop(g, groups).ok && nb_plan_dgrad(g, groups).ok ? 1 : 0;
+}
+
 extern "C" int b200gan_nb_supported(const b200gan_conv_geom *g) {
   if (!g || validate_geom(g) != B200GAN_OK) return 0;
   if (g->transposed || g->up != 1 || g->pad_mode != B200GAN_PAD_ZERO) return 0;
@@ -1195,8 +1232,10 @@ extern "C" int b200gan_nb_supported(const b200gan_conv_geom *g) {
 namespace b200gan {
 static int nb_fprop2_launch(const b200gan_conv_geom *g, const NbBn &in_bn, float *rm, float *rv, long long *nbt,
                             float momentum, const float *x, const float *packed, const float *bias, int act, float slope,
-                            const float *chan_scale, float *y, double *out_stats, int reflect, int rtf, cudaStream_t st) {
-  const NbPlan pl = nb_plan_fprop(g);
+                            const float *chan_scale, float *y, double *out_stats, int reflect, int rtf, int groups,
+                            cudaStream_t st) {
+  B2_CHECK_ARG(groups >= 1 && groups <= NB_MAX_GROUPS && g->N % groups == 0, "nb_fprop: bad statistics group count");
+  const NbPlan pl = nb_plan_fprop(g, groups);
   B2_CHECK_ARG(pl.ok, "nb_fprop: no tile plan fits in shared memory");
   NbFprop2 q;
   q.x = x; q.wp = packed; q.bias = bias; q.cs = chan_scale; q.y = y; q.out_stats = out_stats;
@@ -1209,6 +1248,7 @@ static int nb_fprop2_launch(const b200gan_conv_geom *g, const NbBn &in_bn, float
   q.CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
   q.reflect = reflect;
   q.rtf = rtf;
+  q.groups = groups;
   dim3 grid((unsigned)(ceil_div(g->N, pl.t.TN) * pl.t.tiles_r * pl.t.tiles_q), (unsigned)(g->K / pl.t.KB));
 #define NB_FPROP_CASE(KT_, PT_)                                                                              \
   if (pl.KT == KT_ && pl.PT == PT_) {                                                                        \
@@ -1242,19 +1282,23 @@ int nb_plain_fprop(const b200gan_conv_geom *g, const b200gan_epilogue *ep, const
   NbBn none = to_bn(nullptr);
   return nb_fprop2_launch(g, none, nullptr, nullptr, nullptr, 0.f, x, packed, ep ? ep->bias : nullptr,
                           ep ? ep->act : B200GAN_ACT_NONE, ep ? ep->slope : 0.f, ep ? ep->chan_scale : nullptr, y, nullptr,
-                          g->pad_mode == B200GAN_PAD_REFLECT ? 1 : 0, ep ? ep->round_tf32 : 0, st);
+                          g->pad_mode == B200GAN_PAD_REFLECT ? 1 : 0, ep ? ep->round_tf32 : 0, 1, st);
 }
 }  // namespace b200gan
 
 extern "C" int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn, float *running_mean,
                                 float *running_var, int64_t *num_batches_tracked, float momentum, const float *x,
                                 const float *packed, const float *bias, int32_t act, float slope, const float *chan_scale,
-                                float *y, double *out_stats, void *stream) {
+                                float *y, double *out_stats, int32_t groups, void *stream) {
   B2_CHECK_ARG(b200gan_nb_supported(g), "nb_fprop: unsupported geometry");
+  if (groups < 1) groups = 1;
+  B2_CHECK_ARG(!(in_bn && in_bn->stats) || (in_bn->groups > 1 ? in_bn->groups : 1) == groups,
+               "nb_fprop: the input edge and the call disagree on the statistics group count");
+  B2_CHECK_ARG(groups == 1 || !nb_v1(), "nb_fprop: statistics groups need the staged kernels");
   B2_CHECK_ARG(x && packed && y, "nb_fprop: null pointer");
   B2_CHECK_ARG((((uintptr_t)x | (uintptr_t)packed | (uintptr_t)y) & 15) == 0, "nb_fprop: pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
-  if (out_stats) B2_CUDA(cudaMemsetAsync(out_stats, 0, (size_t)2 * g->K * sizeof(double), st));
+  if (out_stats) B2_CUDA(cudaMemsetAsync(out_stats, 0, (size_t)groups * 2 * g->K * sizeof(double), st));
   const int64_t M = (int64_t)g->N * g->P * g->Q;
   if (M == 0) return B200GAN_OK;
   NbFprop p;
@@ -1265,7 +1309,7 @@ extern "C" int b200gan_nb_fprop(const b200gan_conv_geom *g, const b200gan_nb_bn 
   p.stride = g->stride; p.pad_t = g->pad_t; p.pad_l = g->pad_l; p.slope = slope; p.act = act;
   if (!nb_v1())
     return nb_fprop2_launch(g, p.in_bn, p.rm, p.rv, p.nbt, momentum, x, packed, bias, act, slope, chan_scale, y, out_stats,
-                            0, 0, st);
+                            0, 0, groups, st);
   // v1 (B200GAN_NB_V1=1): direct gathers from global memory
   const int KT = (g->K % 8 == 0 && M * (g->K / 8) >= 148 * 512) ? 8 : 4;
   p.Mpad = (int)(ceil_div64(M, 256) * 256);
@@ -1288,10 +1332,12 @@ extern "C" int b200gan_nb_dz(int32_t N, int64_t PQ, int32_t K, const float *g, c
   p.g = g; p.a = a; p.cs = chan_scale; p.dz = dz; p.db = db; p.out_bn = to_bn(out_bn); p.sums = sums;
   p.rows = (int64_t)N * PQ; p.PQ = PQ; p.K = K; p.slope = slope; p.act = act;
   const int rows_per_block = 256 / (K / 4);
-  int64_t blocks = ceil_div64(p.rows, rows_per_block * 4);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  const int groups = p.out_bn.stats ? p.out_bn.groups : 1;
+  B2_CHECK_ARG(N % groups == 0, "nb_dz: the batch must split evenly into the statistics groups");
+  int64_t blocks = ceil_div64(p.rows / groups, rows_per_block * 4);
+  if (blocks > 148 * 4 / groups) blocks = 148 * 4 / groups;
   if (blocks < 1) blocks = 1;
-  nbk_dz_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+  nbk_dz_kernel<<<dim3((unsigned)blocks, (unsigned)groups), 256, 0, st>>>(p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
@@ -1321,6 +1367,9 @@ struct NbWgPlan {
 };
 static NbWgPlan nb_wgrad_plan(const b200gan_conv_geom *g) {
   NbWgPlan w;
+  // room for the scale / shift tables of up to NB_MAX_GROUPS statistics groups, whatever the call uses: the plan (and
+  // with it the workspace size) must not depend on the group count
+  const int groups = g->C <= NB_MAXC ? NB_MAX_GROUPS : 1;
   w.row_mode = (g->R * g->S > 16) ? 1 : 0;
   w.nsets = g->C * ((g->K + 3) / 4) * (w.row_mode ? g->R : 1);
   int spb = 256;
@@ -1346,7 +1395,7 @@ static NbWgPlan nb_wgrad_plan(const b200gan_conv_geom *g) {
     const int PR = (TR - 1) * g->stride + g->R, PC = (TQ - 1) * g->stride + g->S;
     const size_t tables = (size_t)((2 * spb + TN * TR * TQ + 3) & ~3);
     return (tables + (((size_t)TN * PR * PC * g->C + 3) & ~(size_t)3) + (size_t)TN * TR * TQ * ((g->K + 3) / 4 * 4) +
-            2 * ((g->C + 3) & ~3)) * sizeof(float);
+            2 * (size_t)groups * ((g->C + 3) & ~3)) * sizeof(float);
   };
   while (w.TN > 1 && tile_bytes(w.TN, w.TR, w.TQ) > 96 * 1024) w.TN = (w.TN + 1) / 2;
   while (w.TR > 1 && tile_bytes(w.TN, w.TR, w.TQ) > 96 * 1024) w.TR = (w.TR + 1) / 2;
@@ -1391,6 +1440,9 @@ int b200gan::nb_wgrad_run(const b200gan_conv_geom *g, const b200gan_nb_bn *in_bn
     B2_CUDA(cudaMemsetAsync(dw, 0, (size_t)dw_elems * sizeof(float), st));
     return B200GAN_OK;
   }
+  const int groups = (in_bn && in_bn->stats && in_bn->groups > 1) ? in_bn->groups : 1;
+  B2_CHECK_ARG(g->N % groups == 0, "nb_wgrad: the batch must split evenly into the statistics groups");
+  B2_CHECK_ARG(groups == 1 || (groups <= NB_MAX_GROUPS && g->C <= NB_MAXC), "nb_wgrad: too many statistics groups");
   const NbWgPlan w = nb_wgrad_plan(g);
   B2_CHECK_ARG(w.smem <= 96 * 1024, "nb_wgrad: tile does not fit in shared memory");
   const bool use_ws = w.use_ws && workspace != nullptr;
@@ -1437,7 +1489,9 @@ namespace b200gan {
 static int nb_dgrad2_launch(const b200gan_conv_geom *g, const float *dz, const float *packed, const NbBn &in_bn,
                             const float *a_prev, float *g_out, double *sums, cudaStream_t st) {
   const int st_ = g->stride;
-  const NbPlan pl = nb_plan_dgrad(g);
+  const int groups = in_bn.stats ? in_bn.groups : 1;
+  B2_CHECK_ARG(groups <= NB_MAX_GROUPS && g->N % groups == 0, "nb_dgrad: bad statistics group count");
+  const NbPlan pl = nb_plan_dgrad(g, groups);
   B2_CHECK_ARG(pl.ok, "nb_dgrad: no tile plan fits in shared memory");
   NbDgrad2 q;
   q.dz = dz; q.wp = packed; q.a_prev = a_prev; q.g_out = g_out; q.sums = sums; q.in_bn = in_bn;
@@ -1494,7 +1548,9 @@ extern "C" int b200gan_nb_dgrad(const b200gan_conv_geom *g, const float *dz, con
   B2_CHECK_ARG(dz && packed && g_out, "nb_dgrad: null pointer");
   B2_CHECK_ARG(!sums || (in_bn && in_bn->stats && a_prev), "nb_dgrad: sums need the upstream BatchNorm and its input");
   cudaStream_t st = as_stream(stream);
-  if (sums) B2_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * g->C * sizeof(double), st));
+  const int dgroups = (in_bn && in_bn->stats && in_bn->groups > 1) ? in_bn->groups : 1;
+  B2_CHECK_ARG(dgroups == 1 || !nb_v1(), "nb_dgrad: statistics groups need the staged kernels");
+  if (sums) B2_CUDA(cudaMemsetAsync(sums, 0, (size_t)dgroups * 2 * g->C * sizeof(double), st));
   if ((int64_t)g->N * g->H * g->W == 0) return B200GAN_OK;
   NbDgrad p;
   p.dz = dz; p.wp = packed; p.a_prev = a_prev; p.g_out = g_out; p.sums = sums; p.in_bn = to_bn(in_bn);
@@ -1531,7 +1587,10 @@ extern "C" int b200gan_nb_tail_fwd(int32_t N, int32_t HW, int32_t C, const b200g
   p.a = a; p.out = out; p.bn = to_bn(bn); p.rm = running_mean; p.rv = running_var;
   p.nbt = reinterpret_cast<long long *>(num_batches_tracked); p.momentum = momentum;
   p.N = N; p.HW = HW; p.C = C; p.nchw = nchw;
-  nbk_tail_fwd_kernel<<<(unsigned)tail_grid((int64_t)N * HW * C, C), 256, 0, as_stream(stream)>>>(p);
+  const int groups = p.bn.groups;
+  B2_CHECK_ARG(groups <= NB_MAX_GROUPS && N % groups == 0, "nb_tail_fwd: bad statistics group count");
+  nbk_tail_fwd_kernel<<<dim3((unsigned)tail_grid((int64_t)(N / groups) * HW * C, C), (unsigned)groups), 256, 0,
+                        as_stream(stream)>>>(p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
@@ -1542,12 +1601,14 @@ extern "C" int b200gan_nb_tail_bwd(int32_t N, int32_t HW, int32_t C, const b200g
                "nb_tail_bwd: bad arguments");
   B2_CHECK_ARG(256 % C == 0, "nb_tail_bwd: C must divide 256");
   cudaStream_t st = as_stream(stream);
-  B2_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
+  const int groups = (bn->groups > 1) ? bn->groups : 1;
+  B2_CHECK_ARG(groups <= NB_MAX_GROUPS && N % groups == 0, "nb_tail_bwd: bad statistics group count");
+  B2_CUDA(cudaMemsetAsync(sums, 0, (size_t)groups * 2 * C * sizeof(double), st));
   NbTail p;
   memset(&p, 0, sizeof(p));
   p.a = a; p.dout = dout; p.g = g; p.sums = sums; p.bn = to_bn(bn);
   p.N = N; p.HW = HW; p.C = C; p.nchw = nchw;
-  nbk_tail_bwd_kernel<<<(unsigned)tail_grid((int64_t)N * HW * C, C), 256, 0, st>>>(p);
+  nbk_tail_bwd_kernel<<<dim3((unsigned)tail_grid((int64_t)(N / groups) * HW * C, C), (unsigned)groups), 256, 0, st>>>(p);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }

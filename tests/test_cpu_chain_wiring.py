@@ -52,7 +52,8 @@ def emulated(monkeypatch):
         _, _, _, sc, sh = _bn_consts(edge)
         return x.double() * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
 
-    def nb_fprop(g, x, weight, bias, act, slope, chan_scale, in_edge, rm, rv, nbt, momentum, want_stats):
+    def nb_fprop(g, x, weight, bias, act, slope, chan_scale, in_edge, rm, rv, nbt, momentum, want_stats, groups=1):
+        assert groups == 1   # the grouped pass is a GPU-kernel feature (tests/test_gpu_chain.py)
         if in_edge is not None:
             _update_running(in_edge, rm, rv, nbt, momentum)
         z = tf.conv2d(norm_in(x, in_edge), weight.double(), None if bias is None else bias.double(), g.stride, g.pad_t)

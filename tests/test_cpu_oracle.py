@@ -97,7 +97,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.NormDesc) == 9 * 4
     assert ctypes.sizeof(_lib.GpMlpDesc) == 6 * 4
     assert ctypes.sizeof(_lib.TailDesc) == 8 * 4
-    assert ctypes.sizeof(_lib.NbBn) == 40 and ctypes.sizeof(_lib.AdamTensor) == 40
+    assert ctypes.sizeof(_lib.NbBn) == 48 and ctypes.sizeof(_lib.AdamTensor) == 40
     assert ctypes.sizeof(_lib.PackJob) == 16 + 17 * 4 + 4
 
 

@@ -113,3 +113,42 @@ def test_whole_discriminator_real_plus_fake_accumulates():
         ((bce(net(a), ones) + bce(net(b), zeros)) / 2).backward()
     for (name, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
         assert rel_err(po.grad, pr.grad) < 1e-4, name
+
+
+@pytest.mark.parametrize("chans,size,n,groups", [((1, 16, 32, 64, 128), 64, 128, 2), ((1, 16, 32, 64, 128), 32, 8, 2),
+                                                 ((4, 16, 32), 16, 4, 4)])
+def test_grouped_pass_equals_separate_passes_of_stock_torch(chans, size, n, groups):
+    """ops.bn_groups(G): ONE pass of the fused chain over G concatenated batches against G separate forward passes of the
+    stock modules (dcgan.py:178-179: discriminator(real_imgs), discriminator(gen_imgs.detach())) with Dropout2d active
+    and the same seed: outputs, per-pass input gradients, parameter gradients summed over the passes, running
+    statistics and num_batches_tracked after G sequential updates."""
+    from b200gan import nn as bnn, ops
+    ref, ours = _pair(chans)
+    xs = [torch.randn(n, chans[0], size, size, device="cuda") for _ in range(groups)]
+    assert bnn.groups_eligible(ours, (groups * n,) + tuple(xs[0].shape[1:]), groups)
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    torch.manual_seed(77)
+    yr = [ref(x) for x in xr]                       # pass g draws its masks after pass g-1 drew all of its own
+    xo = torch.cat(xs).requires_grad_(True)
+    torch.manual_seed(77)
+    with ops.bn_groups(groups):
+        yo = ours(xo)
+    assert rel_err(yo, torch.cat(yr)) < 1e-4
+    gy = [torch.randn_like(y) for y in yr]
+    for y, g in zip(yr, gy):
+        y.backward(g)
+    yo.backward(torch.cat(gy))
+    assert rel_err(xo.grad, torch.cat([x.grad for x in xr])) < 1e-4
+    for (name, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert rel_err(po.grad, pr.grad) < 2e-4, name
+    for (name, bo), (_, br) in zip(ours.named_buffers(), ref.named_buffers()):
+        assert rel_err(bo.float(), br.float()) < 1e-4, name
+
+
+def test_groups_refuse_modules_outside_a_fused_chain():
+    from b200gan import nn as bnn, ops
+    bn = bnn.BatchNorm2d(8).cuda().train()
+    with ops.bn_groups(2), pytest.raises(RuntimeError):
+        bn(torch.randn(4, 8, 8, 8, device="cuda"))
+    seq = bnn.Sequential(bnn.Conv2d(256, 256, 3, 1, 1), bnn.BatchNorm2d(256)).cuda().train()   # too wide for the chain
+    assert not bnn.groups_eligible(seq, (4, 256, 8, 8), 2)
