@@ -6,6 +6,8 @@ import contextlib
 
 import torch
 
+from . import ops
+
 
 @contextlib.contextmanager
 def frozen(module):
