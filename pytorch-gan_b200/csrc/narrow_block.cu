@@ -1144,7 +1144,7 @@ struct NbPlan {
 // grid can fill.
 template <class F>
 static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, int nclasses, bool allow_pt, int groups,
-                      F patch) {
+                      bool nclasses_is_dgrad, F patch) {
   NbPlan best;
   memset(&best, 0, sizeof(best));
   double best_cost = 1e30;
@@ -1154,12 +1154,17 @@ static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, in
   else if (nout % 4 == 0) kts[0] = 4;
   else if (nout == 3 || nout == 6) kts[0] = nout;   // image-side data gradients: all channels of a pixel in one thread
   else kts[0] = 1;
+  // tuning hook (tools/nb_sweep.py): B200GAN_NB_FORCE_{FPROP,DGRAD}="KT:PT:KG" restricts the search to one candidate
+  int fkt = 0, fpt = 0, fkg = 0;
+  if (const char *f = getenv(nclasses_is_dgrad ? "B200GAN_NB_FORCE_DGRAD" : "B200GAN_NB_FORCE_FPROP"))
+    if (sscanf(f, "%d:%d:%d", &fkt, &fpt, &fkg) != 3) fkt = fpt = fkg = 0;
   for (int ki = 0; ki < 3 && kts[ki]; ++ki) {
     const int KT = kts[ki];
-    for (int PT = allow_pt ? 4 : 1; PT >= 1; PT /= 2) {
+    for (int PT = (allow_pt || fpt > 1) ? 4 : 1; PT >= 1; PT /= 2) {
       for (int KG = 8; KG >= 1; KG /= 2) {
         const int KB = KG * KT;
         if (KB > nout || nout % KB != 0) continue;
+        if (fkt && (KT != fkt || PT != fpt || KG != fkg)) continue;
         NbTile t;
         t.KG = KG; t.KB = KB; t.TP = PT * (256 / KG);
         t.TQ = pow2ceil(Wo) < 32 ? pow2ceil(Wo) : 32;
@@ -1192,7 +1197,7 @@ static NbPlan nb_plan(int nout, int64_t wrow, int cin, int N, int Ho, int Wo, in
 }
 static NbPlan nb_plan_fprop(const b200gan_conv_geom *g, int groups = 1) {
   const int CP = (g->C % 4 == 0) ? g->C + 4 : g->C;
-  return nb_plan(g->K, (int64_t)g->R * g->S * g->C, g->C, g->N, g->P, g->Q, 1, g->R * g->S * g->C >= 16, groups,
+  return nb_plan(g->K, (int64_t)g->R * g->S * g->C, g->C, g->N, g->P, g->Q, 1, g->R * g->S * g->C >= 16, groups, false,
                  [&](int TN, int TR, int TQ) {
     return (size_t)TN * ((TR - 1) * g->stride + g->R) * ((TQ - 1) * g->stride + g->S) * CP;
   });
@@ -1201,7 +1206,7 @@ static NbPlan nb_plan_dgrad(const b200gan_conv_geom *g, int groups = 1) {
   const int st = g->stride;
   const int Rm = ceil_div(g->R, st), Sm = ceil_div(g->S, st);
   return nb_plan(g->C, (int64_t)Rm * Sm * g->K, g->C, g->N, ceil_div(g->H, st), ceil_div(g->W, st), st * st, g->C >= 4,
-                 groups, [&](int TN, int TR, int TQ) { return (size_t)TN * (TR + Rm - 1) * (TQ + Sm - 1) * (g->K + 4); });
+                 groups, true, [&](int TN, int TR, int TQ) { return (size_t)TN * (TR + Rm - 1) * (TQ + Sm - 1) * (g->K + 4); });
 }
 }  // namespace b200gan
 

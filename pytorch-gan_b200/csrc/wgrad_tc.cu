@@ -231,6 +231,58 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, float *__
   }
 }
 
+
+// Tile version: the partial matrices are contiguous along one channel dimension ("col"), the parameter layout along the
+// taps and then the OTHER or the same channel dimension -- element-wise, consecutive threads wrote 4 bytes every R*S*4
+// bytes (28 us per U-Net layer, 0.57 ms per Pix2Pix step).  A block moves a 32 (col) x 8 (row) x taps tile through shared
+// memory: 128-byte reads per (row, tap), contiguous runs of 8*R*S or 32*R*S floats out.
+constexpr int WR_COL = 32, WR_ROW = 8, WR_TAPS = 16;
+__global__ void __launch_bounds__(256)
+wgrad_reduce_tile_kernel(const float *__restrict__ partial, float *__restrict__ dw, WgReduceP p) {
+  __shared__ float s[WR_ROW][WR_COL][WR_TAPS + 1];
+  const int RS = p.R * p.S;
+  const int tin = p.up2 ? 16 : RS;                       // partial matrices (jobs) per weight
+  // partial[job][row][col]: (row, col) = (sch, dch) if s_is_a else (dch, sch); sch = transposed ? k : c, dch = transposed ? c : k
+  const bool col_is_k = (p.s_is_a != 0) != (p.transposed != 0);   // s_is_a: col = dch = (transposed ? c : k)
+  const int ncol = col_is_k ? p.K : p.C, nrow = col_is_k ? p.C : p.K;
+  const int tiles_col = (ncol + WR_COL - 1) / WR_COL;
+  const int col0 = (blockIdx.x % tiles_col) * WR_COL, row0 = (blockIdx.x / tiles_col) * WR_ROW;
+  const int64_t job_stride = (int64_t)p.mtotal * p.ldn;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < WR_COL * WR_ROW * tin; e += 256) {
+    const int cl = e % WR_COL, rw = (e / WR_COL) % WR_ROW, j = e / (WR_COL * WR_ROW);
+    float v = 0.f;
+    if (col0 + cl < ncol && row0 + rw < nrow) v = __ldg(partial + j * job_stride + (int64_t)(row0 + rw) * p.ldn + col0 + cl);
+    s[rw][cl][j] = v;
+  }
+  __syncthreads();
+  // dw[(A * NB + B) * RS + t]: (A, B) = (k, c) for Conv2d, (c, k) for ConvTranspose2d
+  const bool col_is_b = col_is_k == (p.transposed != 0);          // inner output dimension B = transposed ? k : c
+  const int nb = p.transposed ? p.K : p.C;
+  for (int e = tid; e < WR_COL * WR_ROW * RS; e += 256) {
+    const int t = e % RS;
+    int cl, rw;
+    if (col_is_b) { cl = (e / RS) % WR_COL; rw = e / (RS * WR_COL); }   // runs of 32 * RS floats
+    else          { rw = (e / RS) % WR_ROW; cl = e / (RS * WR_ROW); }   // runs of 8 * RS floats
+    const int col = col0 + cl, row = row0 + rw;
+    if (col >= ncol || row >= nrow) continue;
+    float acc;
+    if (!p.up2) {
+      acc = s[rw][cl][t];
+    } else {
+      const int r = t / 3, q = t % 3;
+      acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int ph = j >> 2, tp = j & 3;
+        if (up2_contrib(r, ph >> 1, tp >> 1) && up2_contrib(q, ph & 1, tp & 1)) acc += s[rw][cl][j];
+      }
+    }
+    const int a = col_is_b ? row : col, b = col_is_b ? col : row;
+    dw[((int64_t)a * nb + b) * RS + t] = acc;
+  }
+}
+
 // ---- host -------------------------------------------------------------------------------------------
 static int ilog2c(int v) {
   int l = 0;
@@ -418,6 +470,15 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   rp.K = g->K; rp.C = g->C; rp.R = g->R; rp.S = g->S; rp.njobs = pl.njobs;
   rp.s_is_a = pl.s_is_a; rp.up2 = up2 ? 1 : 0; rp.transposed = g->transposed ? 1 : 0; rp.mtotal = pl.mtotal; rp.ldn = pl.ldn;
   int64_t total = (int64_t)g->K * g->C * g->R * g->S;
+  static const bool tiled = !(getenv("B200GAN_WG_REDUCE_TILED") && atoi(getenv("B200GAN_WG_REDUCE_TILED")) == 0);
+  if (tiled && g->R * g->S <= WR_TAPS && g->K >= 32 && g->C >= 32) {
+    const bool col_is_k = (pl.s_is_a != 0) != (g->transposed != 0);
+    const int ncol = col_is_k ? g->K : g->C, nrow = col_is_k ? g->C : g->K;
+    const unsigned tiles = (unsigned)(ceil_div(ncol, WR_COL) * ceil_div(nrow, WR_ROW));
+    wgrad_reduce_tile_kernel<<<tiles, 256, 0, st>>>(ws, dw, rp);
+    B2_LAUNCH_CHECK();
+    return B200GAN_OK;
+  }
   unsigned blocks = (unsigned)(ceil_div64(total, 256) > 2368 ? 2368 : ceil_div64(total, 256));
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, rp);
   B2_LAUNCH_CHECK();
