@@ -32,7 +32,9 @@ CASES = [(2, 128, 16, 16, 3, 4, (2, 2, 1, 1), 2, False),     # pix2pix generator
          (2, 512, 8, 8, 1, 4, (2, 2, 1, 1), 1, False),       # patch discriminator output
          (2, 64, 16, 16, 3, 7, (3, 3, 3, 3), 1, True),       # cyclegan generator output layer
          (2, 64, 20, 12, 1, 3, (1, 1, 1, 1), 1, False),      # dcgan generator output layer (un-fused form)
-         (1, 32, 10, 10, 2, 3, (1, 1, 1, 1), 2, False),
+         (1, 32, 10, 10, 2, 3, (1, 1, 1, 1), 2, False),      # 3x3 behind the x2 upsample: folded taps, odd padding parity
+         (2, 64, 8, 12, 3, 4, (1, 1, 2, 2), 2, False),       # 4x4 folded, odd padding parity
+         (2, 128, 7, 5, 1, 4, (2, 2, 1, 1), 2, False),       # folded, ragged, one output channel
          (2, 256, 6, 6, 4, 3, (1, 1, 1, 1), 1, False)]
 
 
