@@ -190,9 +190,11 @@ __device__ __forceinline__ float pack_element(const PackJob &j, long long i) {
 // rest of the sector is needed by blocks far away (measured: 557 us for the 54 M U-Net weights, 1.5 TB/s of useful
 // traffic).  Here a block loads whole contiguous runs (8 input channels x all taps of one output channel = 512 B for a
 // 4x4 filter) into shared memory and writes 128-byte (order 0) / 32-byte (order 1) segments per tap.
-__device__ __forceinline__ void pack_tile(const PackJob &j, int tile) {
-  __shared__ float s[PACK_CO_T][PACK_CI_T * PACK_RS_MAX + 1];
-  const int RS = j.R * j.S;
+// RS_ = R * S as a compile-time constant (16: 4x4, 9: 3x3; 0: run time): every index decomposition below divides by it, and
+// with run-time divisors the kernel was bound by integer division (no faster than the element-wise gather)
+template <int RS_>
+__device__ __forceinline__ void pack_tile(const PackJob &j, int tile, float (*s)[PACK_CI_T * PACK_RS_MAX + 1]) {
+  const int RS = RS_ ? RS_ : j.R * j.S;
   const int tci = tile % j.tiles_ci, tco = tile / j.tiles_ci;
   const int co0 = tco * PACK_CO_T, ci0 = tci * PACK_CI_T;
   const int tid = threadIdx.x;
@@ -252,7 +254,12 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
   }
   const PackJob &j = tb.job[lo];
   if (j.tiles_ci > 0) {
-    pack_tile(j, (int)blockIdx.x - tb.block_begin[lo]);
+    __shared__ float s[PACK_CO_T][PACK_CI_T * PACK_RS_MAX + 1];
+    const int tile = (int)blockIdx.x - tb.block_begin[lo];
+    const int rs = j.R * j.S;
+    if (rs == 16) pack_tile<16>(j, tile, s);
+    else if (rs == 9) pack_tile<9>(j, tile, s);
+    else pack_tile<0>(j, tile, s);
     return;
   }
   const long long i0 = (long long)((int)blockIdx.x - tb.block_begin[lo]) * PACK_CHUNK;

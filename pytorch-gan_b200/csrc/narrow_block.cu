@@ -222,7 +222,6 @@ __device__ __forceinline__ void nb_stage(float *dst, int CP, const float *src_im
                                          int H, int W, const float *sc_s, const float *sh_s, bool reflect, int tid) {
   if ((C & 3) == 0) {
     const int C4 = C >> 2, total = rows * cols * C4;
-#pragma unroll 4   // independent iterations: four loads in flight per thread instead of one round trip at a time
     for (int i = tid; i < total; i += 256) {
       const int c4 = i % C4, pix = i / C4;
       const int pc = pix % cols, pr = pix / cols;
@@ -243,7 +242,6 @@ __device__ __forceinline__ void nb_stage(float *dst, int CP, const float *src_im
     }
   } else {
     const int total = rows * cols * C;
-#pragma unroll 4
     for (int i = tid; i < total; i += 256) {
       const int cc = i % C, pix = i / C;
       const int pc = pix % cols, pr = pix / cols;
@@ -548,7 +546,7 @@ struct NbWgrad {
 // grid = (persistent blocks over tiles, set chunks).
 // dynamic smem: patch [TN][PR][PC][C] | dz tile [TN*TR*TQ][K4*4] | sc, sh [C] | pixel offsets [TN*TR*TQ] | set bases [SPB]
 template <int TAPS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)   // two blocks per SM: 148 registers (one block per SM) cost 40 % on the 4x4 layers
 nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
   extern __shared__ __align__(16) float nsm[];
   const int tile_px = p.TN * p.TR * p.TQ;
@@ -620,7 +618,6 @@ nbk_wgrad_kernel(const __grid_constant__ NbWgrad p) {
     }
     const int img_px = p.TR * p.TQ;
     if ((p.K & 3) == 0) {
-#pragma unroll 4
       for (int i = tid; i < tile_px * K4; i += 256) {
         const int k4 = i % K4, pix = i / K4;
         const int li = pix / img_px, rem = pix - li * img_px;
