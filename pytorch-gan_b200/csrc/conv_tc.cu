@@ -130,10 +130,16 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];  // sum over the 32 lanes of column `lane`
 }
 
-template <int BN, int STAGES>
+// CL = 2: launched as clusters of two CTAs along x (two neighbouring pixel tiles of the same output-channel tile).  Both
+// need the same weight (B) box every iteration: each CTA fetches HALF of it and multicasts it into both shared memories, so
+// the weights cross L2 -> SM once per pair (at BN = 256 the per-CTA re-fetch of B was 2/3 of the 906 MB a 256->256 residual
+// conv pulls through L2, and L2 -> SM bandwidth, ~10 TB/s, is what the kernel ran at).  A stage is free again only when BOTH
+// CTAs' MMAs on it have retired: the MMA warps commit to the empty barrier of both CTAs (count 2).
+template <int BN, int STAGES, int CL = 1>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ TcParams p) {
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ TcParams p,
+               const __grid_constant__ CUtensorMap tmBh) {
   constexpr int B_BYTES = BN * TC_BK * 4;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -167,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -176,6 +182,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  uint32_t crank = 0;
+  if (CL == 2) {
+    crank = cluster_ctarank();
+    cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
+  }
   const uint32_t tmem = *tmem_ptr;
   if (threadIdx.x == 0) TC_TRACE(1);
 
@@ -193,7 +204,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (it < 16) TC_TRACE(2 + it);
         mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
         tma_load_5d(sa, &tmA, &full[stage], tp.dc + kc * TC_BK, w0 + tp.dw, tp.da, h0 + tp.dh, n0);
-        tma_load_3d(sb, &tmB, &full[stage], kc * TC_BK, ntile * BN, tp.bt);
+        if (CL == 2)   // rows [crank * BN/2, +BN/2) of the B box, into both CTAs
+          tma_load_3d_mc(sb + crank * (B_BYTES / 2), &tmBh, &full[stage], kc * TC_BK, ntile * BN + (int)crank * (BN / 2), tp.bt,
+                         (uint16_t)3);
+        else
+          tma_load_3d(sb, &tmB, &full[stage], kc * TC_BK, ntile * BN, tp.bt);
         if (++kc == p.kchunks) {
           kc = 0;
           ++tap;
@@ -222,7 +237,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
           umma_tf32(tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+        if (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)3);   // ... in both CTAs of the pair
+        else umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -372,6 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
     tmem_dealloc<BN>(tmem);
   }
+  if (CL == 2) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers
   if (threadIdx.x == 0) TC_TRACE(42);
 }
 
@@ -654,11 +671,28 @@ static int ilog2_ceil(int v) {
 
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmY, const TcParams &p, dim3 grid,
-                     cudaStream_t st) {
+                     cudaStream_t st, const CUtensorMap *tmBh = nullptr) {
   constexpr int SMEM = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + 4 * BN * 2 * 4;
+  if (tmBh) {   // clusters of two CTAs along x sharing the weight boxes (see conv_tc_kernel)
+    static std::atomic<uint64_t> attr_done2{0};
+    if (int e = ensure_dynamic_smem(conv_tc_kernel<BN, STAGES, 2>, SMEM, attr_done2)) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, 2>, tmA, tmB, tmY, p, *tmBh));
+    return B200GAN_OK;
+  }
   static std::atomic<uint64_t> attr_done{0};
-  if (int e = ensure_dynamic_smem(conv_tc_kernel<BN, STAGES>, SMEM, attr_done)) return e;
-  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, tmY, p);
+  if (int e = ensure_dynamic_smem(conv_tc_kernel<BN, STAGES, 1>, SMEM, attr_done)) return e;
+  conv_tc_kernel<BN, STAGES, 1><<<grid, TC_THREADS, SMEM, st>>>(tmA, tmB, tmY, p, tmB);
   B2_LAUNCH_CHECK();
   return B200GAN_OK;
 }
@@ -849,9 +883,21 @@ static int run_tc(const float *in, int N, int Hi, int Wi, int Cc, bool phase_in,
     if (int e = make_tmap_f32(&tmB, packedB, 3, dims, strides, box)) return e;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * ceil_div(N, BNn)), (unsigned)(Kout / BN), (unsigned)(nphase * p.ksplit));
+  // pairs of neighbouring pixel tiles share their weight boxes through a cluster multicast (wide tiles only: that is where
+  // the weights dominate the operand traffic)
+  CUtensorMap tmBh;
+  const CUtensorMap *pair = nullptr;
+  static const int cluster_mode = getenv("B200GAN_TC_CLUSTER") ? atoi(getenv("B200GAN_TC_CLUSTER")) : 0;
+  if (cluster_mode && !narrow_k && BN >= 128 && grid.x % 2 == 0 && grid.x >= 2) {
+    uint64_t dims[3] = {(uint64_t)Cc, (uint64_t)Kreal, (uint64_t)btaps};
+    uint64_t strides[2] = {(uint64_t)Cc * 4, (uint64_t)Kreal * Cc * 4};
+    uint32_t box[3] = {TC_BK, (uint32_t)(BN / 2), 1};
+    if (int e = make_tmap_f32(&tmBh, packedB, 3, dims, strides, box)) return e;
+    pair = &tmBh;
+  }
   int rc;
-  if (BN == 256) rc = launch_tc<256, 2>(tmA, tmB, tmY, p, grid, st);
-  else if (BN == 128) rc = launch_tc<128, 3>(tmA, tmB, tmY, p, grid, st);
+  if (BN == 256) rc = launch_tc<256, 2>(tmA, tmB, tmY, p, grid, st, pair);
+  else if (BN == 128) rc = launch_tc<128, 3>(tmA, tmB, tmY, p, grid, st, pair);
   else if (BN == 64) rc = launch_tc<64, 4>(tmA, tmB, tmY, p, grid, st);
   else rc = launch_tc<32, 4>(tmA, tmB, tmY, p, grid, st);
   if (rc == B200GAN_OK && deferred_stats) {
