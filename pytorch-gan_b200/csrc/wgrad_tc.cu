@@ -157,30 +157,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
+    // The staging tile reuses the pipeline buffers, which hold at most 128 columns x 128 rows (NB = 256 with two stages:
+    // 96 KB): rounds of 128 columns, each stored before the next one overwrites the staging area.
+    constexpr int ROUND = NB < 128 ? NB : 128;
+    const int row0 = job * p.mtotal + mt * 128;
 #pragma unroll 1
-    for (int c = 0; c < NB; c += 32) {
-      float v[32];
-      if (iters > 0) {
-        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      } else {
+    for (int r0 = 0; r0 < NB; r0 += ROUND) {
+#pragma unroll 1
+      for (int c = r0; c < r0 + ROUND; c += 32) {
+        float v[32];
+        if (iters > 0) {
+          tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        uint8_t *row = smem + ((c - r0) >> 5) * 16384 + m * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4 *>(row + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-      uint8_t *row = smem + (c >> 5) * 16384 + m * 128;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4 *>(row + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    fence_proxy_async();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 64) {
-      // all pixel splits of a job accumulate into the same [job][M'][N'] tile: TMA reduce-add (fp32 add at L2)
-      const int row0 = job * p.mtotal + mt * 128;
-      if (iters > 0) {
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64 && iters > 0) {
+        // all pixel splits of a job accumulate into the same [job][M'][N'] tile: TMA reduce-add (fp32 add at L2)
 #pragma unroll 1
-        for (int c = 0; c < NB; c += 32) tma_reduce_add_2d(&tmP, smem + (c >> 5) * 16384, nt * NB + c, row0);
+        for (int c = r0; c < r0 + ROUND; c += 32) tma_reduce_add_2d(&tmP, smem + ((c - r0) >> 5) * 16384, nt * NB + c, row0);
         tma_store_commit_and_wait_read();
       }
+      if (NB > ROUND) asm volatile("bar.sync 1, 128;" ::: "memory");   // the staging area is read before it is reused
     }
   }
   tc_fence_before();
@@ -328,6 +333,10 @@ static bool wg_plan(const b200gan_conv_geom *g, WgPlan &pl) {
   else return false;
   const int mch = pl.s_is_a ? pl.sch : pl.dch, nch = pl.s_is_a ? pl.dch : pl.sch;
   pl.NB = nch % 128 == 0 ? 128 : (nch % 64 == 0 ? 64 : 32);
+  // 128 x 256 output tiles: the 128-channel operand is re-read half as often.  The kernel is L2 -> SM bound (a 256 -> 256
+  // 3x3 layer pulls 9 jobs x 4 tiles x 33 MB = 1.2 GB through L2 in 132 us with 128 x 128 tiles).
+  static const int nb256 = getenv("B200GAN_WG_NB256") ? atoi(getenv("B200GAN_WG_NB256")) : 0;
+  if (nb256 && nch % 256 == 0) pl.NB = 256;
   pl.mtotal = mch;
   pl.ldn = nch;
   pl.mtiles = mch / 128;
@@ -460,7 +469,8 @@ int tc_wgrad(const b200gan_conv_geom *g, const float *x, const float *dy, float 
   }
   B2_CUDA(cudaMemsetAsync(ws, 0, (size_t)pl.njobs * pl.mtotal * pl.ldn * sizeof(float), st));
   dim3 grid((unsigned)pl.nsplits, (unsigned)pl.njobs, (unsigned)(pl.mtiles * pl.ntiles));
-  int rc = pl.NB == 128 ? (pl.pix == 64 ? launch_wg<128, 2, 64>(tmX, tmY, tmP, p, grid, st)
+  int rc = pl.NB == 256 ? launch_wg<256, 2, 32>(tmX, tmY, tmP, p, grid, st)
+           : pl.NB == 128 ? (pl.pix == 64 ? launch_wg<128, 2, 64>(tmX, tmY, tmP, p, grid, st)
                                         : launch_wg<128, 3, 32>(tmX, tmY, tmP, p, grid, st))
            : pl.NB == 64 ? (pl.pix == 64 ? launch_wg<64, 2, 64>(tmX, tmY, tmP, p, grid, st)
                                          : launch_wg<64, 4, 32>(tmX, tmY, tmP, p, grid, st))
