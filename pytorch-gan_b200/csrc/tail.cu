@@ -341,33 +341,8 @@ __device__ __forceinline__ void load_gn(const float *__restrict__ g, int64_t pix
   }
 }
 
-// The same nine neighbours, fetched ONCE per pixel: lane t < 9 of the C4 lanes that share the pixel loads tap t (one guarded
-// load instead of nine per lane), a shuffle inside the lane group hands every tap to every lane.  (ncu, final build: the
-// reduce pass executed 281 instructions per 4-channel pixel slice, a third of them these guarded loads.)
-template <int KK, int C4>
-__device__ __forceinline__ void load_gn_group(const float *__restrict__ g, int64_t pix, int h, int w, int H, int W,
-                                              float (&gn)[KK][9], int c4, int ps) {
-  if (C4 < 9) {
-    load_gn<KK>(g, pix, h, w, H, W, gn);
-    return;
-  }
-  const unsigned gmask = C4 >= 32 ? 0xffffffffu : (((1u << (C4 & 31)) - 1u) << (ps * C4));
-  const int gbase = ps * C4;
-  float mine[KK];
-  {
-    const int r = c4 / 3, s_ = c4 - 3 * r;
-    const int hh = h + 1 - r, ww = w + 1 - s_;
-    const bool ok = c4 < 9 && hh >= 0 && hh < H && ww >= 0 && ww < W;
-    const int64_t off = pix + (int64_t)(1 - r) * W + (1 - s_);
-#pragma unroll
-    for (int k = 0; k < KK; ++k) mine[k] = ok ? __ldg(g + off * KK + k) : 0.f;
-  }
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int k = 0; k < KK; ++k) gn[k][t] = __shfl_sync(gmask, mine[k], gbase + t);
-}
-
+// (Tried: lane t < 9 of the pixel's lane group loads tap t and a shuffle hands it round -- one guarded load instead of nine
+// per lane.  Measured slower, 250 vs 224 us for the backward pair: the nine dependent shuffles sit on the load latency.)
 // pass 1: BatchNorm-backward sums + the conv's weight / bias gradient.  C4 lanes cover one pixel (float4 each).
 template <int C4, int KK>
 __global__ void __launch_bounds__(RB_THREADS, KK == 1 ? 2 : 1)
@@ -442,7 +417,7 @@ tail_bwd_reduce_kernel(const __grid_constant__ TailBwdP p) {
         int w, h;
         tail_hw(cw0 + lp, ch0, W, H, wsh, w, h);
         float gn[KK][9];
-        load_gn_group<KK, C4>(p.g, pix, h, w, H, W, gn, c4, ps);
+        load_gn<KK>(p.g, pix, h, w, H, W, gn);
         const float x[4] = {av.x, av.y, av.z, av.w};
         float pre[4], y[4], dy[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -582,7 +557,7 @@ tail_bwd_apply_kernel(const __grid_constant__ TailBwdP p) {
       int w, h;
       tail_hw(cw0 + lp, ch0, W, H, wsh, w, h);
       float gn[KK][9];
-      load_gn_group<KK, C4>(p.g, pix, h, w, H, W, gn, c4, ps);
+      load_gn<KK>(p.g, pix, h, w, H, W, gn);
       const float x[4] = {av.x, av.y, av.z, av.w};
       float dy[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
