@@ -169,3 +169,28 @@ def test_patch_dispatches_adam_and_resets_pack_caches_on_apply():
         sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda e: 1.0)         # cyclegan.py:93-101 still works
         assert sched.get_last_lr() == [2e-4]
     assert torch.optim.Adam is stock_adam and torch.nn.Module.apply.__qualname__ == "Module.apply"
+
+
+def test_grouped_discriminator_pass_eligibility_is_decided_on_the_host():
+    """train.dcgan_step batches discriminator(real) and discriminator(fake) (dcgan.py:178-179) into one grouped pass only
+    when the fused chain covers the whole conv stack at that shape AND every layer has a tile plan whose tiles stay inside
+    one statistics group (b200gan_nb_groups_supported: host-side planner, no GPU needed)."""
+    import ctypes
+    from b200gan import _lib, nn as bnn, ops, zoo
+    d = zoo.DCGANDiscriminator(64)
+    assert bnn.groups_eligible(d.model, (256, 1, 64, 64), 2)          # BASELINE: 2 x 128 images
+    assert bnn.groups_eligible(d.model, (64, 1, 32, 32), 2)
+    assert not bnn.groups_eligible(d.model, (255, 1, 64, 64), 2)      # does not split evenly
+    assert not bnn.groups_eligible(d.model, (256, 3, 64, 64), 2)      # wrong channel count: the chain does not qualify
+    wide = bnn.Sequential(bnn.Conv2d(256, 256, 3, 1, 1), bnn.BatchNorm2d(256))
+    assert not bnn.groups_eligible(wide, (4, 256, 8, 8), 2)           # tensor-core territory, not a fused chain
+    assert ops.bn_groups.active == 1                                  # the probe leaves no state behind
+    lib = _lib.load()
+    g, _ = ops.make_geom((6, 64, 8, 8), (128, 64, 3, 3), 2, (1, 1, 1, 1))
+    assert lib.b200gan_nb_supported(ctypes.byref(g)) == 1
+    # 3 images per group at 16 output pixels each: every plan needs tiles of >= 2 images, which would straddle the groups
+    assert lib.b200gan_nb_groups_supported(ctypes.byref(g), 2) == 0
+    assert lib.b200gan_nb_groups_supported(ctypes.byref(g), 1) == 1
+    g2, _ = ops.make_geom((8, 64, 8, 8), (128, 64, 3, 3), 2, (1, 1, 1, 1))
+    assert lib.b200gan_nb_groups_supported(ctypes.byref(g2), 2) == 1
+    assert lib.b200gan_nb_groups_supported(ctypes.byref(g2), 5) == 0  # more groups than the kernels take
